@@ -1,0 +1,158 @@
+/*
+ * mandalorion_poa.h -- C ABI of the B200-native consensus library (libmandalorion_poa.so).
+ *
+ * This is the drop-in boundary for Mandalorion's per-isoform consensus step.  The
+ * reference has no FFI: the interface it replaces is the subprocess protocol
+ *
+ *     abpoa -M 5 -r 0 [-S] <in.fasta>  >  <consensus.fasta>
+ *
+ * issued once per isoform by determine_consensus()
+ * (reference utils/SpliceDefineConsensus.py:917 and :919, called from
+ * defineIsoforms.py:89).  One call of mpoa_consensus_batch() replaces MANY of those
+ * subprocess calls: every group is one "in.fasta" (reads in file order), every
+ * consensus one ">Consensus_sequence" record.
+ *
+ * Conventions: plain pointers and sizes; every buffer is caller-owned; return value
+ * 0 = ok, negative = MPOA_E*; no exceptions cross the ABI; a context is bound to one
+ * CUDA device and is not thread-safe (one context per host thread / GPU).
+ * There is no CPU path behind this ABI: mpoa_create() fails when no CUDA device is
+ * usable.
+ */
+#ifndef MANDALORION_POA_H
+#define MANDALORION_POA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPOA_ABI_VERSION 1
+
+/* error codes (negative return values) */
+#define MPOA_OK          0
+#define MPOA_EINVAL     -1   /* bad argument */
+#define MPOA_ENODEV     -2   /* no usable CUDA device / CUDA error at create */
+#define MPOA_ECUDA      -3   /* CUDA runtime error, see mpoa_last_error() */
+#define MPOA_ENOSPC     -4   /* cons_buf too small; cons_off[n_groups] holds the need */
+#define MPOA_ENOMEM     -5   /* device/host allocation failed */
+
+/* per-group status written to group_status[] */
+#define MPOA_GROUP_OK       0  /* consensus produced */
+#define MPOA_GROUP_EMPTY    1  /* no consensus (abpoa would have printed nothing or died):
+                                  caller falls back to the first read, reference
+                                  utils/SpliceDefineConsensus.py:924-925 */
+
+/* group_flags bits */
+#define MPOA_FLAG_SEED   1u    /* the reference would have passed -S (median read length
+                                  >= 8000, utils/SpliceDefineConsensus.py:916-919) */
+
+/*
+ * Scoring / band parameters == the abpoa command line of the reference.
+ * mpoa_default_params() fills the values of "abpoa -M 5 -r 0":
+ *   match 5, mismatch 4, convex gap (4,2)/(24,1), adaptive band b=10 f=0.01.
+ * simd_pn_i16 / simd_pn_i32: abPOA rounds every band to whole SIMD vectors, so the
+ * band (and in rare ties the result) depends on the vector width of the abpoa BUILD
+ * the reference would have run: 8/4 (SSE4.1), 16/8 (AVX2, the released binary and
+ * the default here), 32/16 (AVX512BW).
+ */
+typedef struct mpoa_params {
+    int32_t match;
+    int32_t mismatch;
+    int32_t gap_open1, gap_ext1;
+    int32_t gap_open2, gap_ext2;
+    int32_t wb;
+    float   wf;
+    int32_t simd_pn_i16;
+    int32_t simd_pn_i32;
+    int32_t reserved[6];
+} mpoa_params;
+
+/* Work accounting of one batch call (all counters are sums over the batch). */
+typedef struct mpoa_stats {
+    int64_t n_groups;        /* groups processed                                         */
+    int64_t n_reads;         /* reads consumed                                           */
+    int64_t n_alignments;    /* read-to-graph alignments (reads 2..n of every group)     */
+    int64_t band_cells;      /* DP cells inside the adaptive band (the GCUPS numerator)  */
+    int64_t full_cells;      /* sum of graph_rows x (qlen+1): full-matrix equivalent     */
+    int64_t int_ops;         /* 17*band_cells + 3*sum((in_degree-1)*row_cells)           */
+    int64_t n_align_i16;     /* alignments abPOA would have run in int16 lanes           */
+    int64_t n_align_i32;     /* ... in int32 lanes                                       */
+    int64_t tb_bytes;        /* traceback bytes written to HBM                           */
+    int64_t n_retry_groups;  /* groups re-run with a larger device workspace             */
+    double  kernel_ms;       /* device time of the POA kernel(s), CUDA events            */
+    double  h2d_ms;          /* host->device copies (0 for the *_device entry point)     */
+    double  d2h_ms;          /* device->host copies                                      */
+    int64_t n_kernel_launches; /* kernels of this library launched by the call           */
+    int64_t reserved[4];
+} mpoa_stats;
+
+/*
+ * Optional per-read trace for parity tests (any pointer may be NULL).  Nodes are named
+ * by their creator: the index of the read base (relative to the first base of the
+ * group) that created the node, which is independent of internal node numbering.
+ */
+typedef struct mpoa_trace {
+    int32_t *read_score;      /* [n_reads]  best global score, 0 for the first read       */
+    int32_t *read_bits;       /* [n_reads]  16 or 32: abPOA's lane width, 0 first read    */
+    int64_t *read_band_cells; /* [n_reads]                                                */
+    int32_t *base_aln;        /* [n_bases]  creator of the node this base was aligned to
+                                            (cigar MATCH target), -1 = insertion          */
+    int32_t *base_node;       /* [n_bases]  creator of the node the base was merged into
+                                            (== own index when it created a node)         */
+} mpoa_trace;
+
+typedef struct mpoa_ctx mpoa_ctx;
+
+int  mpoa_abi_version(void);
+void mpoa_default_params(mpoa_params *p);
+
+/* device_ordinal: CUDA device index (>= 0).  Returns MPOA_ENODEV without a GPU. */
+int  mpoa_create(mpoa_ctx **out, int device_ordinal, const mpoa_params *p);
+void mpoa_destroy(mpoa_ctx *ctx);
+const char *mpoa_last_error(mpoa_ctx *ctx);
+
+/* Kernels are launched on this stream (a cudaStream_t); default is the legacy stream. */
+int  mpoa_set_stream(mpoa_ctx *ctx, void *cuda_stream);
+
+/* enable != 0: the next mpoa_batch_upload() also allocates the per-read trace arrays. */
+int  mpoa_set_trace(mpoa_ctx *ctx, int enable);
+
+/*
+ * Consensus of n_groups independent read groups, HOST buffers in, HOST buffers out.
+ *   group_read_off[n_groups+1]  reads of group g are [group_read_off[g], group_read_off[g+1])
+ *   read_base_off[n_reads+1]    bases of read r are bases[read_base_off[r] .. read_base_off[r+1])
+ *   bases                       ASCII, any case; everything except ACGTacgt is N
+ *   group_flags[n_groups]       MPOA_FLAG_* or NULL
+ *   cons_off[n_groups+1]  (out) consensus of group g is cons_buf[cons_off[g] .. cons_off[g+1])
+ *   cons_buf / cons_cap   (out) ASCII "ACGTN", no terminator
+ *   group_status[n_groups] (out) MPOA_GROUP_*
+ *   stats, trace          (out) nullable
+ * Reads of a group are aligned IN THE GIVEN ORDER (progressive POA is order dependent,
+ * reference order comes from utils/SpliceDefineConsensus.py:884-888).  Groups of one
+ * read return that read; the reference's "<= 2 reads" bypass (:911-912) is the
+ * caller's decision, the library aligns whatever it is given.
+ */
+int  mpoa_consensus_batch(mpoa_ctx *ctx, int64_t n_groups,
+                          const int64_t *group_read_off, const int64_t *read_base_off,
+                          const uint8_t *bases, const uint8_t *group_flags,
+                          int64_t *cons_off, uint8_t *cons_buf, int64_t cons_cap,
+                          int32_t *group_status, mpoa_stats *stats, mpoa_trace *trace);
+
+/*
+ * Same job split in three so that a caller can keep the inputs resident in HBM:
+ *   mpoa_batch_upload : host -> device copy of the group arrays + scheduling
+ *   mpoa_batch_run    : kernels only (may be called repeatedly on the same upload)
+ *   mpoa_batch_fetch  : device -> host copy of the consensus sequences
+ */
+int  mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups,
+                       const int64_t *group_read_off, const int64_t *read_base_off,
+                       const uint8_t *bases, const uint8_t *group_flags);
+int  mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats);
+int  mpoa_batch_fetch(mpoa_ctx *ctx, int64_t *cons_off, uint8_t *cons_buf, int64_t cons_cap,
+                      int32_t *group_status, mpoa_trace *trace);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MANDALORION_POA_H */

@@ -1,0 +1,477 @@
+/*
+ * poa_capi.cu -- host side of libmandalorion_poa.so: the C ABI declared in
+ * include/mandalorion_poa.h.  Batching, length binning, device workspace, launch and retry
+ * logic around the kernels of poa_kernels.cu.  There is no CPU compute path here: every
+ * consensus is produced by poa_group_kernel.
+ *
+ * One call of mpoa_consensus_batch() stands for many `abpoa -M 5 -r 0 in.fasta` processes
+ * of the reference (utils/SpliceDefineConsensus.py:917), one per group.
+ */
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/mandalorion_poa.h"
+#include "poa_device.cuh"
+
+namespace mpoa {
+cudaError_t launch_encode(const uint8_t *ascii, uint8_t *codes, int64_t n, cudaStream_t stream);
+cudaError_t launch_poa(const KernelArgs &A, int n_blocks, int warps_per_block, cudaStream_t stream);
+int poa_max_blocks_per_sm(int wcap, int warps_per_block);
+size_t poa_smem_bytes(int wcap, int warps_per_block);
+cudaError_t launch_gather(const uint8_t *cons, const int64_t *region_off, const int32_t *cons_len,
+                          const int64_t *out_off, uint8_t *out, int64_t n_groups, cudaStream_t stream);
+}  // namespace mpoa
+
+using namespace mpoa;
+
+struct GroupInfo {
+    int32_t n_reads, maxlen, minlen;
+    int64_t sumlen;
+    double cost;
+    int32_t wneed;
+};
+
+struct mpoa_ctx {
+    int dev = 0;
+    int n_sm = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    mpoa_params params;
+    std::string err;
+    int want_trace = 0;
+    /* uploaded batch */
+    int64_t n_groups = 0, n_reads = 0, n_bases = 0;
+    std::vector<int64_t> h_gro, h_rbo;
+    std::vector<GroupInfo> ginfo;
+    uint8_t *d_codes = nullptr;
+    int64_t *d_rbo = nullptr, *d_gro = nullptr, *d_region_off = nullptr;
+    uint8_t *d_cons = nullptr;
+    int32_t *d_cons_len = nullptr, *d_status = nullptr, *d_queue = nullptr;
+    int *d_queue_head = nullptr;
+    unsigned long long *d_stats = nullptr;
+    int32_t *d_tr_score = nullptr, *d_tr_bits = nullptr, *d_tr_aln = nullptr, *d_tr_node = nullptr;
+    long long *d_tr_cells = nullptr;
+    uint8_t *d_ws = nullptr;
+    size_t ws_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double h2d_ms = 0;
+    bool ran = false;
+    std::vector<int32_t> h_status;
+    mpoa_stats last;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e);                         \
+            return _e == cudaErrorMemoryAllocation ? MPOA_ENOMEM : MPOA_ECUDA;                     \
+        }                                                                                          \
+    } while (0)
+
+static void free_batch(mpoa_ctx *ctx) {
+    cudaFree(ctx->d_codes); cudaFree(ctx->d_rbo); cudaFree(ctx->d_gro); cudaFree(ctx->d_region_off);
+    cudaFree(ctx->d_cons); cudaFree(ctx->d_cons_len); cudaFree(ctx->d_status); cudaFree(ctx->d_queue);
+    cudaFree(ctx->d_tr_score); cudaFree(ctx->d_tr_bits); cudaFree(ctx->d_tr_aln); cudaFree(ctx->d_tr_node);
+    cudaFree(ctx->d_tr_cells);
+    ctx->d_codes = nullptr; ctx->d_rbo = ctx->d_gro = ctx->d_region_off = nullptr; ctx->d_cons = nullptr;
+    ctx->d_cons_len = ctx->d_status = ctx->d_queue = nullptr;
+    ctx->d_tr_score = ctx->d_tr_bits = ctx->d_tr_aln = ctx->d_tr_node = nullptr; ctx->d_tr_cells = nullptr;
+    ctx->n_groups = ctx->n_reads = ctx->n_bases = 0;
+    ctx->ran = false;
+}
+
+extern "C" int mpoa_abi_version(void) { return MPOA_ABI_VERSION; }
+
+extern "C" void mpoa_default_params(mpoa_params *p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->match = 5; p->mismatch = 4;
+    p->gap_open1 = 4; p->gap_ext1 = 2; p->gap_open2 = 24; p->gap_ext2 = 1;
+    p->wb = 10; p->wf = 0.01f;
+    p->simd_pn_i16 = 16; p->simd_pn_i32 = 8;
+}
+
+extern "C" int mpoa_create(mpoa_ctx **out, int device_ordinal, const mpoa_params *p) {
+    if (!out) return MPOA_EINVAL;
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) return MPOA_ENODEV;
+    if (device_ordinal < 0 || device_ordinal >= n_dev) return MPOA_ENODEV;
+    if (cudaSetDevice(device_ordinal) != cudaSuccess) return MPOA_ENODEV;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess) return MPOA_ENODEV;
+    if (prop.major < 10) return MPOA_ENODEV;  // sm_100a code only
+    mpoa_ctx *ctx = new mpoa_ctx();
+    ctx->dev = device_ordinal;
+    ctx->n_sm = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if (p) ctx->params = *p; else mpoa_default_params(&ctx->params);
+    if (ctx->params.simd_pn_i16 <= 0) ctx->params.simd_pn_i16 = 16;
+    if (ctx->params.simd_pn_i32 <= 0) ctx->params.simd_pn_i32 = 8;
+    if (cudaMalloc(&ctx->d_queue_head, sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_stats, SI_COUNT * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        delete ctx;
+        return MPOA_ENODEV;
+    }
+    *out = ctx;
+    return MPOA_OK;
+}
+
+extern "C" void mpoa_destroy(mpoa_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->dev);
+    free_batch(ctx);
+    cudaFree(ctx->d_ws);
+    cudaFree(ctx->d_queue_head);
+    cudaFree(ctx->d_stats);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    delete ctx;
+}
+
+extern "C" const char *mpoa_last_error(mpoa_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int mpoa_set_stream(mpoa_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return MPOA_EINVAL;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return MPOA_OK;
+}
+
+extern "C" int mpoa_set_trace(mpoa_ctx *ctx, int enable) {
+    if (!ctx) return MPOA_EINVAL;
+    ctx->want_trace = enable ? 1 : 0;
+    return MPOA_OK;
+}
+
+extern "C" int mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups, const int64_t *group_read_off,
+                                 const int64_t *read_base_off, const uint8_t *bases, const uint8_t *group_flags) {
+    (void)group_flags;  // MPOA_FLAG_SEED: the unseeded alignment is run for every group (scope)
+    if (!ctx || n_groups < 0) return MPOA_EINVAL;
+    if (n_groups > 0 && (!group_read_off || !read_base_off)) { ctx->err = "null offsets"; return MPOA_EINVAL; }
+    CK(cudaSetDevice(ctx->dev));
+    free_batch(ctx);
+    if (n_groups == 0) return MPOA_OK;
+    if (n_groups > INT_MAX / 2) { ctx->err = "too many groups"; return MPOA_EINVAL; }
+    const int64_t n_reads = group_read_off[n_groups];
+    if (group_read_off[0] != 0 || n_reads < 0) { ctx->err = "group_read_off must start at 0"; return MPOA_EINVAL; }
+    const int64_t n_bases = n_reads > 0 ? read_base_off[n_reads] : 0;
+    if (n_reads > 0 && (read_base_off[0] != 0 || n_bases < 0 || (n_bases > 0 && !bases))) {
+        ctx->err = "bad read_base_off / bases";
+        return MPOA_EINVAL;
+    }
+    ctx->h_gro.assign(group_read_off, group_read_off + n_groups + 1);
+    ctx->h_rbo.assign(read_base_off, read_base_off + n_reads + 1);
+    ctx->ginfo.resize(n_groups);
+    for (int64_t g = 0; g < n_groups; ++g) {
+        GroupInfo &gi = ctx->ginfo[g];
+        const int64_t r0 = ctx->h_gro[g], r1 = ctx->h_gro[g + 1];
+        if (r1 < r0 || r1 > n_reads) { ctx->err = "group_read_off not monotone"; return MPOA_EINVAL; }
+        gi.n_reads = (int32_t)(r1 - r0);
+        gi.maxlen = 0; gi.minlen = INT_MAX; gi.sumlen = 0;
+        for (int64_t r = r0; r < r1; ++r) {
+            const int64_t len = ctx->h_rbo[r + 1] - ctx->h_rbo[r];
+            if (len < 0 || len > (1 << 26)) { ctx->err = "bad read length"; return MPOA_EINVAL; }
+            gi.maxlen = std::max<int32_t>(gi.maxlen, (int32_t)len);
+            gi.minlen = std::min<int32_t>(gi.minlen, (int32_t)len);
+            gi.sumlen += len;
+        }
+        if (gi.n_reads == 0) gi.minlen = 0;
+        /* expected band: 2w + length spread + SIMD rounding on both sides + slack */
+        const int w = ctx->params.wb + (int)(ctx->params.wf * (float)gi.maxlen);
+        gi.wneed = 2 * w + (gi.maxlen - gi.minlen) + 2 * ctx->params.simd_pn_i16 + 48;
+        gi.cost = (double)gi.sumlen * (double)gi.wneed;
+    }
+    ctx->n_groups = n_groups; ctx->n_reads = n_reads; ctx->n_bases = n_bases;
+
+    cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;
+    CK(cudaEventRecord(e0, ctx->stream));
+    uint8_t *d_ascii = nullptr;
+    const size_t nb = (size_t)std::max<int64_t>(n_bases, 16);
+    CK(cudaMalloc(&d_ascii, nb));
+    CK(cudaMalloc(&ctx->d_codes, nb));
+    CK(cudaMalloc(&ctx->d_rbo, (n_reads + 1) * sizeof(int64_t)));
+    CK(cudaMalloc(&ctx->d_gro, (n_groups + 1) * sizeof(int64_t)));
+    CK(cudaMalloc(&ctx->d_region_off, (n_groups + 1) * sizeof(int64_t)));
+    CK(cudaMalloc(&ctx->d_cons, nb));
+    CK(cudaMalloc(&ctx->d_cons_len, n_groups * sizeof(int32_t)));
+    CK(cudaMalloc(&ctx->d_status, n_groups * sizeof(int32_t)));
+    CK(cudaMalloc(&ctx->d_queue, n_groups * sizeof(int32_t)));
+    if (n_bases > 0) CK(cudaMemcpyAsync(d_ascii, bases, n_bases, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_rbo, ctx->h_rbo.data(), (n_reads + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_gro, ctx->h_gro.data(), (n_groups + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    /* consensus region of a group = the byte range of its reads: a consensus is a path of the
+     * graph and can never hold more nodes than the group has bases */
+    std::vector<int64_t> region(n_groups + 1);
+    for (int64_t g = 0; g <= n_groups; ++g) region[g] = ctx->h_rbo[ctx->h_gro[g]];
+    CK(cudaMemcpyAsync(ctx->d_region_off, region.data(), (n_groups + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_encode(d_ascii, ctx->d_codes, n_bases, ctx->stream));
+    if (ctx->want_trace) {
+        CK(cudaMalloc(&ctx->d_tr_score, std::max<int64_t>(n_reads, 1) * sizeof(int32_t)));
+        CK(cudaMalloc(&ctx->d_tr_bits, std::max<int64_t>(n_reads, 1) * sizeof(int32_t)));
+        CK(cudaMalloc(&ctx->d_tr_cells, std::max<int64_t>(n_reads, 1) * sizeof(long long)));
+        CK(cudaMalloc(&ctx->d_tr_aln, nb * sizeof(int32_t)));
+        CK(cudaMalloc(&ctx->d_tr_node, nb * sizeof(int32_t)));
+    }
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    ctx->h2d_ms = ms;
+    cudaFree(d_ascii);
+    return MPOA_OK;
+}
+
+/* capacities of one launch */
+struct Caps {
+    uint32_t ncap, ecap, qcap;
+    uint64_t tbcap, spcap;
+    int wcap;
+};
+
+static uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+static SlotLayout make_layout(const Caps &c) {
+    SlotLayout L;
+    std::memset(&L, 0, sizeof(L));
+    L.ncap = c.ncap; L.ecap = c.ecap; L.qcap = c.qcap; L.tbcap = c.tbcap; L.spcap = c.spcap;
+    uint64_t off = 0;
+    auto take = [&](uint64_t bytes) { uint64_t o = off; off = align_up(off + bytes, 256); return o; };
+    const uint64_t n = c.ncap + 2, e = c.ecap + 2, q = c.qcap + 2;
+    for (int p = 0; p < 2; ++p) {
+        L.base[p] = take(n); L.sib[p] = take(n); L.creator[p] = take(n * 4);
+        L.in_off[p] = take(n * 4); L.in_row[p] = take(e * 4);
+        L.out_off[p] = take(n * 4); L.out_row[p] = take(e * 4); L.out_w[p] = take(e * 4);
+    }
+    L.remain = take(n * 4); L.meta = take(n * 4); L.rowinfo = take(n * 16); L.tboff = take(n * 4);
+    L.rowbest = take(n * 4); L.spoff = take(n * 4); L.qmap = take(q * 4);
+    L.pv = take(q * 4); L.pkey = take(q * 4); L.pnew = take(q * 4); L.psib = take(q * 4);
+    L.nin = take(q * 4); L.nout = take(q * 4);
+    L.cnt = take(n * 4); L.addin = take(n * 4); L.addout = take(n * 4); L.grow = take(n); L.srcof = take(n * 4);
+    L.tb = take(c.tbcap + 16);
+    L.spill = take(c.spcap * 4 + 16);
+    L.slot_bytes = align_up(off, 1024);
+    return L;
+}
+
+static const int kWcapBins[] = {96, 128, 160, 192, 256, 320, 384, 512, 768, 1024, 1536, 2048, 3072, 4096, 6144, 8192};
+
+static int pick_wcap(int wneed) {
+    for (int b : kWcapBins) if (b >= wneed) return b;
+    return -1;
+}
+
+/* run one set of groups with one set of capacities; appends groups that need more to `retry` */
+static int run_launch(mpoa_ctx *ctx, const std::vector<int32_t> &groups, const Caps &caps, int64_t *n_launch) {
+    if (groups.empty()) return MPOA_OK;
+    /* warps per block: as many (<=4) as the shared-memory ring allows */
+    int wpb = 4;
+    while (wpb > 1 && poa_smem_bytes(caps.wcap, wpb) > ctx->smem_optin) wpb >>= 1;
+    if (poa_smem_bytes(caps.wcap, wpb) > ctx->smem_optin) { ctx->err = "band wider than shared memory allows"; return 1; }
+    int bps = poa_max_blocks_per_sm(caps.wcap, wpb);
+    if (bps <= 0) { ctx->err = "kernel cannot be resident (shared memory)"; return MPOA_ECUDA; }
+    const SlotLayout L = make_layout(caps);
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t avail = (uint64_t)free_b + ctx->ws_bytes;
+    int64_t n_blocks = (int64_t)bps * ctx->n_sm;
+    const int64_t need_blocks = ((int64_t)groups.size() + wpb - 1) / wpb;
+    n_blocks = std::min(n_blocks, need_blocks);
+    const uint64_t budget = (uint64_t)(avail * 0.85);
+    if ((uint64_t)n_blocks * wpb * L.slot_bytes > budget) n_blocks = (int64_t)(budget / ((uint64_t)wpb * L.slot_bytes));
+    if (n_blocks <= 0) { ctx->err = "not enough device memory for one workspace slot"; return 1; }
+    const uint64_t need = (uint64_t)n_blocks * wpb * L.slot_bytes;
+    if (need > ctx->ws_bytes) {
+        cudaFree(ctx->d_ws);
+        ctx->d_ws = nullptr; ctx->ws_bytes = 0;
+        CK(cudaMalloc(&ctx->d_ws, need));
+        ctx->ws_bytes = need;
+    }
+    CK(cudaMemcpyAsync(ctx->d_queue, groups.data(), groups.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_queue_head, 0, sizeof(int), ctx->stream));
+    KernelArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.codes = ctx->d_codes; A.read_off = ctx->d_rbo; A.group_read_off = ctx->d_gro;
+    A.queue = ctx->d_queue; A.n_queue = (int)groups.size(); A.queue_head = ctx->d_queue_head;
+    A.ws = ctx->d_ws; A.L = L;
+    A.cons = ctx->d_cons; A.cons_off = ctx->d_region_off; A.cons_len = ctx->d_cons_len; A.status = ctx->d_status;
+    A.stats = ctx->d_stats;
+    A.tr_score = ctx->d_tr_score; A.tr_bits = ctx->d_tr_bits; A.tr_cells = ctx->d_tr_cells;
+    A.tr_aln = ctx->d_tr_aln; A.tr_node = ctx->d_tr_node;
+    const mpoa_params &p = ctx->params;
+    A.P.match = std::abs(p.match); A.P.mismatch = std::abs(p.mismatch);
+    A.P.o1 = p.gap_open1; A.P.e1 = p.gap_ext1; A.P.o2 = p.gap_open2; A.P.e2 = p.gap_ext2;
+    A.P.oe1 = p.gap_open1 + p.gap_ext1; A.P.oe2 = p.gap_open2 + p.gap_ext2;
+    A.P.wb = p.wb; A.P.wf = p.wf; A.P.pn16 = p.simd_pn_i16; A.P.pn32 = p.simd_pn_i32;
+    A.wcap = caps.wcap;
+    CK(launch_poa(A, (int)n_blocks, wpb, ctx->stream));
+    ++*n_launch;
+    return MPOA_OK;
+}
+
+extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
+    if (!ctx) return MPOA_EINVAL;
+    CK(cudaSetDevice(ctx->dev));
+    mpoa_stats st;
+    std::memset(&st, 0, sizeof(st));
+    st.n_groups = ctx->n_groups; st.n_reads = ctx->n_reads;
+    st.h2d_ms = ctx->h2d_ms;
+    const int64_t ng = ctx->n_groups;
+    ctx->h_status.assign(ng, ST_PENDING);
+    if (ng == 0) { ctx->ran = true; ctx->last = st; if (stats) *stats = st; return MPOA_OK; }
+    CK(cudaMemsetAsync(ctx->d_stats, 0, SI_COUNT * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_cons_len, 0, ng * sizeof(int32_t), ctx->stream));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+
+    std::vector<int32_t> pending(ng);
+    std::iota(pending.begin(), pending.end(), 0);
+    int64_t n_launch = 0;
+    const int kMaxAttempt = 4;
+    for (int attempt = 0; attempt < kMaxAttempt && !pending.empty(); ++attempt) {
+        /* bin by ring width; inside a bin the heaviest groups go first */
+        std::vector<std::pair<int, std::vector<int32_t>>> bins;
+        for (int32_t g : pending) {
+            const GroupInfo &gi = ctx->ginfo[g];
+            int wneed = gi.wneed;
+            for (int a = 0; a < attempt; ++a) wneed = wneed * 3 + 64;
+            int wc = pick_wcap(std::min(wneed, gi.maxlen + 1 + 2 * ctx->params.simd_pn_i16));
+            if (wc < 0) wc = kWcapBins[sizeof(kWcapBins) / sizeof(int) - 1];
+            auto it = std::find_if(bins.begin(), bins.end(), [&](const auto &b) { return b.first == wc; });
+            if (it == bins.end()) { bins.push_back({wc, {}}); it = bins.end() - 1; }
+            it->second.push_back(g);
+        }
+        std::sort(bins.begin(), bins.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+        for (auto &bin : bins) {
+            auto &gs = bin.second;
+            std::sort(gs.begin(), gs.end(), [&](int32_t a, int32_t b) {
+                const double ca = ctx->ginfo[a].cost, cb = ctx->ginfo[b].cost;
+                return ca != cb ? ca > cb : a < b;
+            });
+            Caps c;
+            c.wcap = bin.first;
+            uint64_t ncap = 0, qcap = 0, sum_max = 0;
+            for (int32_t g : gs) {
+                const GroupInfo &gi = ctx->ginfo[g];
+                uint64_t est;
+                if (attempt == 0) est = (uint64_t)(gi.maxlen * (1.0 + 0.03 * gi.n_reads)) + 32ull * gi.n_reads + 256;
+                else if (attempt == 1) est = (uint64_t)(gi.maxlen * (1.0 + 0.15 * gi.n_reads)) + 64ull * gi.n_reads + 1024;
+                else est = (uint64_t)gi.sumlen + 2;
+                est = std::min<uint64_t>(est, (uint64_t)gi.sumlen + 2);
+                ncap = std::max(ncap, est);
+                qcap = std::max<uint64_t>(qcap, gi.maxlen);
+                sum_max = std::max<uint64_t>(sum_max, gi.sumlen);
+            }
+            c.ncap = (uint32_t)std::min<uint64_t>(ncap + 8, 0x7fffff00u);
+            c.ecap = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(2ull * c.ncap + 64, sum_max + 4096), 0x7fffff00u);
+            if (attempt >= 2) c.ecap = (uint32_t)std::min<uint64_t>(sum_max + 4096, 0x7fffff00u);
+            c.qcap = (uint32_t)qcap + 8;
+            const uint64_t wfull = std::min<uint64_t>((uint64_t)c.wcap, qcap + 1 + 64);
+            c.tbcap = std::min<uint64_t>((uint64_t)c.ncap * wfull * (attempt == 0 ? 2 : 4), 0xfff00000ull);
+            c.spcap = std::min<uint64_t>((uint64_t)c.ncap * wfull * 3 / (attempt == 0 ? 8 : (attempt == 1 ? 2 : 1)) + 4096, 0x3ff00000ull);
+            int rc = run_launch(ctx, gs, c, &n_launch);
+            if (rc < 0) return rc;
+            if (rc > 0) {  // cannot be run with these capacities at all: treated like an abpoa failure
+                for (int32_t g : gs) ctx->h_status[g] = ST_EMPTY;
+                gs.clear();
+            }
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        /* collect statuses of what was launched */
+        std::vector<int32_t> dstat(ng);
+        CK(cudaMemcpy(dstat.data(), ctx->d_status, ng * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        std::vector<int32_t> next;
+        for (int32_t g : pending) {
+            if (ctx->h_status[g] == ST_EMPTY) continue;  // not launchable
+            if (dstat[g] == ST_RETRY) next.push_back(g);
+            else ctx->h_status[g] = dstat[g];
+        }
+        if (attempt == 0) st.n_retry_groups = (int64_t)next.size();
+        pending.swap(next);
+    }
+    for (int32_t g : pending) ctx->h_status[g] = ST_EMPTY;  // still too big after the last attempt
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    unsigned long long hs[SI_COUNT];
+    CK(cudaMemcpy(hs, ctx->d_stats, sizeof(hs), cudaMemcpyDeviceToHost));
+    st.kernel_ms = ms;
+    st.band_cells = (int64_t)hs[SI_CELLS]; st.int_ops = (int64_t)hs[SI_INTOPS]; st.full_cells = (int64_t)hs[SI_FULL];
+    st.n_alignments = (int64_t)hs[SI_ALN]; st.n_align_i16 = (int64_t)hs[SI_ALN16]; st.n_align_i32 = (int64_t)hs[SI_ALN32];
+    st.tb_bytes = (int64_t)hs[SI_TB];
+    st.n_kernel_launches = n_launch;
+    ctx->last = st;
+    ctx->ran = true;
+    if (stats) *stats = st;
+    return MPOA_OK;
+}
+
+extern "C" int mpoa_batch_fetch(mpoa_ctx *ctx, int64_t *cons_off, uint8_t *cons_buf, int64_t cons_cap,
+                                int32_t *group_status, mpoa_trace *trace) {
+    if (!ctx || !cons_off) return MPOA_EINVAL;
+    if (!ctx->ran) { ctx->err = "mpoa_batch_fetch before mpoa_batch_run"; return MPOA_EINVAL; }
+    CK(cudaSetDevice(ctx->dev));
+    const int64_t ng = ctx->n_groups;
+    cons_off[0] = 0;
+    if (ng == 0) return MPOA_OK;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    std::vector<int32_t> len(ng);
+    CK(cudaMemcpyAsync(len.data(), ctx->d_cons_len, ng * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int64_t g = 0; g < ng; ++g) {
+        const bool ok = ctx->h_status[g] == ST_OK;
+        cons_off[g + 1] = cons_off[g] + (ok ? len[g] : 0);
+        if (group_status) group_status[g] = ok ? MPOA_GROUP_OK : MPOA_GROUP_EMPTY;
+    }
+    const int64_t total = cons_off[ng];
+    int rc = MPOA_OK;
+    if (total > cons_cap || (total > 0 && !cons_buf)) rc = MPOA_ENOSPC;
+    else if (total > 0) {
+        int64_t *d_out_off = nullptr;
+        uint8_t *d_out = nullptr;
+        CK(cudaMalloc(&d_out_off, (ng + 1) * sizeof(int64_t)));
+        CK(cudaMalloc(&d_out, total));
+        CK(cudaMemcpyAsync(d_out_off, cons_off, (ng + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(launch_gather(ctx->d_cons, ctx->d_region_off, ctx->d_cons_len, d_out_off, d_out, ng, ctx->stream));
+        CK(cudaMemcpyAsync(cons_buf, d_out, total, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_out_off);
+        cudaFree(d_out);
+        ctx->last.n_kernel_launches += 1;
+    }
+    if (trace && ctx->want_trace) {
+        const int64_t nr = ctx->n_reads, nb = ctx->n_bases;
+        if (trace->read_score) CK(cudaMemcpy(trace->read_score, ctx->d_tr_score, nr * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (trace->read_bits) CK(cudaMemcpy(trace->read_bits, ctx->d_tr_bits, nr * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (trace->read_band_cells) CK(cudaMemcpy(trace->read_band_cells, ctx->d_tr_cells, nr * sizeof(long long), cudaMemcpyDeviceToHost));
+        if (trace->base_aln) CK(cudaMemcpy(trace->base_aln, ctx->d_tr_aln, nb * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (trace->base_node) CK(cudaMemcpy(trace->base_node, ctx->d_tr_node, nb * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last.d2h_ms = ms;
+    return rc;
+}
+
+extern "C" int mpoa_consensus_batch(mpoa_ctx *ctx, int64_t n_groups, const int64_t *group_read_off,
+                                    const int64_t *read_base_off, const uint8_t *bases, const uint8_t *group_flags,
+                                    int64_t *cons_off, uint8_t *cons_buf, int64_t cons_cap, int32_t *group_status,
+                                    mpoa_stats *stats, mpoa_trace *trace) {
+    if (!ctx) return MPOA_EINVAL;
+    const int saved = ctx->want_trace;
+    if (trace) ctx->want_trace = 1;
+    int rc = mpoa_batch_upload(ctx, n_groups, group_read_off, read_base_off, bases, group_flags);
+    if (rc == MPOA_OK) rc = mpoa_batch_run(ctx, nullptr);
+    if (rc == MPOA_OK) rc = mpoa_batch_fetch(ctx, cons_off, cons_buf, cons_cap, group_status, trace);
+    ctx->want_trace = saved;
+    if (stats) *stats = ctx->last;
+    return rc;
+}

@@ -1,0 +1,74 @@
+/*
+ * poa_device.cuh -- shared device-side declarations of the B200 consensus kernels.
+ *
+ * What is computed: the partial-order-alignment consensus that Mandalorion obtains from
+ * `abpoa -M 5 -r 0 in.fasta` (reference utils/SpliceDefineConsensus.py:917), for many
+ * independent read groups at once.  How it is laid out is ours:
+ *
+ *   - one WARP owns one read group from the first read to the consensus (reads of a group are
+ *     sequentially dependent, groups are independent); warps pull groups from a global queue
+ *     sorted by descending cost;
+ *   - the POA graph lives in ROW space: nodes are stored in a topological order in which
+ *     aligned-node groups are contiguous, adjacency is CSR with edges in first-creation order.
+ *     After every read the graph is re-emitted (double buffered) with the new nodes merged in,
+ *     so there is never a BFS re-sort; abPOA's results do not depend on which valid
+ *     topological order is used (every tie-break iterates edge lists, never row numbers);
+ *   - DP rows H/E1/E2 live in a per-warp shared-memory ring; rows with a far successor are
+ *     additionally spilled to HBM;
+ *   - traceback is flag based: 1 byte per band cell (4 for rows with several predecessors).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mpoa {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int NEG = -(1 << 28);  // -inf surrogate of the int32 path
+constexpr int RING = 8;          // rows kept in the shared-memory ring
+constexpr int WARPS_PER_BLOCK = 4;
+
+enum GroupStatus : int { ST_OK = 0, ST_EMPTY = 1, ST_RETRY = 2, ST_PENDING = 3 };
+
+struct DevParams {
+    int match, mismatch, o1, e1, o2, e2, oe1, oe2, wb;
+    float wf;
+    int pn16, pn32;
+};
+
+/* byte offsets of the arrays inside one warp's HBM workspace ("slot") */
+struct SlotLayout {
+    uint32_t ncap, ecap, qcap;
+    uint64_t tbcap, spcap;
+    uint64_t base[2], sib[2], creator[2], in_off[2], in_row[2], out_off[2], out_row[2], out_w[2];
+    uint64_t remain, meta, rowinfo, tboff, rowbest, spoff, qmap;
+    uint64_t pv, pkey, pnew, psib, nin, nout;          // per query position
+    uint64_t cnt, addin, addout, grow, srcof;          // per row
+    uint64_t tb, spill;
+    uint64_t slot_bytes;
+};
+
+struct KernelArgs {
+    const uint8_t *codes;            // nt4 codes of all bases of the batch
+    const int64_t *read_off;         // [n_reads+1]
+    const int64_t *group_read_off;   // [n_groups+1]
+    const int32_t *queue;            // group indices to process, heaviest first
+    int n_queue;
+    int *queue_head;
+    uint8_t *ws;                     // n_slots * L.slot_bytes
+    SlotLayout L;
+    uint8_t *cons;                   // consensus bytes, region of group g at cons_off[g]
+    const int64_t *cons_off;
+    int32_t *cons_len;
+    int32_t *status;
+    unsigned long long *stats;       // see StatIdx
+    int32_t *tr_score, *tr_bits;     // optional trace (NULL when off)
+    long long *tr_cells;
+    int32_t *tr_aln, *tr_node;
+    DevParams P;
+    int wcap;                        // cells per ring row
+};
+
+enum StatIdx { SI_CELLS = 0, SI_INTOPS, SI_FULL, SI_ALN, SI_ALN16, SI_ALN32, SI_TB, SI_COUNT };
+
+}  // namespace mpoa

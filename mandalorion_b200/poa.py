@@ -1,0 +1,210 @@
+"""ctypes binding of libmandalorion_poa.so (C ABI: include/mandalorion_poa.h).
+
+The library replaces the `abpoa -M 5 -r 0 [-S] in.fasta` subprocess of the reference
+(utils/SpliceDefineConsensus.py:917,919).  This module only marshals buffers; it never
+computes a consensus itself and raises PoaError when the CUDA library or a GPU is missing.
+"""
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def library_path():
+    return os.path.join(_HERE, "libmandalorion_poa.so")
+
+
+class PoaError(RuntimeError):
+    pass
+
+
+class _Params(C.Structure):
+    _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("gap_open1", C.c_int32), ("gap_ext1", C.c_int32),
+                ("gap_open2", C.c_int32), ("gap_ext2", C.c_int32), ("wb", C.c_int32), ("wf", C.c_float),
+                ("simd_pn_i16", C.c_int32), ("simd_pn_i32", C.c_int32), ("reserved", C.c_int32 * 6)]
+
+
+class _Stats(C.Structure):
+    _fields_ = [("n_groups", C.c_int64), ("n_reads", C.c_int64), ("n_alignments", C.c_int64),
+                ("band_cells", C.c_int64), ("full_cells", C.c_int64), ("int_ops", C.c_int64),
+                ("n_align_i16", C.c_int64), ("n_align_i32", C.c_int64), ("tb_bytes", C.c_int64),
+                ("n_retry_groups", C.c_int64), ("kernel_ms", C.c_double), ("h2d_ms", C.c_double),
+                ("d2h_ms", C.c_double), ("n_kernel_launches", C.c_int64), ("reserved", C.c_int64 * 4)]
+
+
+class _Trace(C.Structure):
+    _fields_ = [("read_score", C.c_void_p), ("read_bits", C.c_void_p), ("read_band_cells", C.c_void_p),
+                ("base_aln", C.c_void_p), ("base_node", C.c_void_p)]
+
+
+@dataclass
+class PoaParams:
+    """Defaults are the reference's command line `abpoa -M 5 -r 0` (utils/SpliceDefineConsensus.py:917)."""
+    match: int = 5
+    mismatch: int = 4
+    gap_open1: int = 4
+    gap_ext1: int = 2
+    gap_open2: int = 24
+    gap_ext2: int = 1
+    wb: int = 10
+    wf: float = 0.01
+    simd_pn_i16: int = 16
+    simd_pn_i32: int = 8
+
+
+_lib = None
+
+# every symbol include/mandalorion_poa.h declares
+ABI_SYMBOLS = ("mpoa_abi_version", "mpoa_default_params", "mpoa_create", "mpoa_destroy", "mpoa_last_error",
+               "mpoa_set_stream", "mpoa_set_trace", "mpoa_consensus_batch", "mpoa_batch_upload", "mpoa_batch_run",
+               "mpoa_batch_fetch")
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise PoaError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback for the consensus path)")
+        lib = C.CDLL(path)
+        lib.mpoa_abi_version.restype = C.c_int
+        lib.mpoa_last_error.restype = C.c_char_p
+        lib.mpoa_last_error.argtypes = [C.c_void_p]
+        lib.mpoa_default_params.argtypes = [C.c_void_p]
+        lib.mpoa_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+        lib.mpoa_destroy.argtypes = [C.c_void_p]
+        lib.mpoa_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        lib.mpoa_set_trace.argtypes = [C.c_void_p, C.c_int]
+        lib.mpoa_batch_upload.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 4
+        lib.mpoa_batch_run.argtypes = [C.c_void_p, C.c_void_p]
+        lib.mpoa_batch_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        lib.mpoa_consensus_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6 + [C.c_int64] + [C.c_void_p] * 3
+        _lib = lib
+    return _lib
+
+
+def pack_groups(groups):
+    """list of groups (each a list of str/bytes reads) -> (group_read_off, read_base_off, bases)."""
+    gro = np.zeros(len(groups) + 1, dtype=np.int64)
+    lens, chunks = [], []
+    for gi, reads in enumerate(groups):
+        gro[gi + 1] = gro[gi] + len(reads)
+        for r in reads:
+            b = r.encode() if isinstance(r, str) else bytes(r)
+            lens.append(len(b))
+            chunks.append(b)
+    rbo = np.zeros(len(lens) + 1, dtype=np.int64)
+    if lens:
+        rbo[1:] = np.cumsum(np.asarray(lens, dtype=np.int64))
+    bases = np.frombuffer(b"".join(chunks), dtype=np.uint8).copy() if chunks else np.zeros(0, dtype=np.uint8)
+    return gro, rbo, bases
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class PoaContext:
+    """One context per (process, GPU); not thread-safe (include/mandalorion_poa.h)."""
+
+    def __init__(self, device=0, params=None):
+        lib = _load()
+        p = params or PoaParams()
+        cp = _Params(p.match, p.mismatch, p.gap_open1, p.gap_ext1, p.gap_open2, p.gap_ext2, p.wb, p.wf,
+                     p.simd_pn_i16, p.simd_pn_i32)
+        h = C.c_void_p()
+        rc = lib.mpoa_create(C.byref(h), int(device), C.byref(cp))
+        if rc != 0:
+            raise PoaError(f"mpoa_create(device={device}) failed with {rc}: a B200 (sm_100) CUDA device is required; "
+                           "there is no CPU fallback")
+        self._h = h
+        self._lib = lib
+        self.device = device
+        self.last_stats = {}
+        self._n = (0, 0, 0)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mpoa_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self._lib.mpoa_last_error(self._h)
+            raise PoaError(f"{what} failed with {rc}: {msg.decode() if msg else ''}")
+
+    def set_stream(self, cuda_stream_handle):
+        self._check(self._lib.mpoa_set_stream(self._h, C.c_void_p(int(cuda_stream_handle))), "mpoa_set_stream")
+
+    def set_trace(self, enable):
+        self._check(self._lib.mpoa_set_trace(self._h, int(bool(enable))), "mpoa_set_trace")
+
+    @staticmethod
+    def _stats_dict(st):
+        return {k: getattr(st, k) for k, _ in _Stats._fields_ if k != "reserved"}
+
+    # ---- three-stage interface (inputs stay resident in HBM between run() calls) ----
+    def upload(self, gro, rbo, bases, flags=None):
+        gro = np.ascontiguousarray(gro, dtype=np.int64)
+        rbo = np.ascontiguousarray(rbo, dtype=np.int64)
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        ng = len(gro) - 1
+        self._check(self._lib.mpoa_batch_upload(self._h, ng, _ptr(gro), _ptr(rbo), _ptr(bases), _ptr(flags)),
+                    "mpoa_batch_upload")
+        self._n = (ng, len(rbo) - 1, int(rbo[-1]) if len(rbo) else 0)
+
+    def run(self):
+        st = _Stats()
+        self._check(self._lib.mpoa_batch_run(self._h, C.byref(st)), "mpoa_batch_run")
+        self.last_stats = self._stats_dict(st)
+        return self.last_stats
+
+    def fetch(self, trace=False):
+        ng, nr, nb = self._n
+        cap = max(16, nb)
+        cons_buf = np.empty(cap, dtype=np.uint8)
+        cons_off = np.zeros(ng + 1, dtype=np.int64)
+        status = np.zeros(ng, dtype=np.int32)
+        tr, arrs = None, None
+        if trace:
+            arrs = dict(read_score=np.zeros(nr, np.int32), read_bits=np.zeros(nr, np.int32),
+                        read_band_cells=np.zeros(nr, np.int64), base_aln=np.full(nb, -9, np.int32),
+                        base_node=np.full(nb, -9, np.int32))
+            tr = _Trace(*[arrs[k].ctypes.data for k in
+                          ("read_score", "read_bits", "read_band_cells", "base_aln", "base_node")])
+        self._check(self._lib.mpoa_batch_fetch(self._h, _ptr(cons_off), _ptr(cons_buf), cap, _ptr(status),
+                                               C.byref(tr) if tr is not None else None), "mpoa_batch_fetch")
+        raw = cons_buf[:cons_off[ng]].tobytes()
+        cons = [raw[cons_off[i]:cons_off[i + 1]] for i in range(ng)]
+        return dict(cons=cons, status=status, cons_off=cons_off, trace=arrs)
+
+    # ---- the one-call interface ----
+    def consensus_batch(self, groups=None, packed=None, trace=False):
+        """groups: list of lists of reads (str/bytes), aligned in the given order.
+        Returns dict(cons=[bytes], status=int32[], stats=dict, trace=dict|None)."""
+        gro, rbo, bases = packed if packed is not None else pack_groups(groups)
+        self.set_trace(trace)
+        try:
+            self.upload(gro, rbo, bases)
+            stats = self.run()
+            out = self.fetch(trace=trace)
+        finally:
+            self.set_trace(False)
+        out["stats"] = stats
+        return out

@@ -1,0 +1,666 @@
+/*
+ * abpoa_oracle.cpp -- CPU oracle: scalar restatement of `abpoa -M 5 -r 0 <in.fasta>`
+ * (abPOA v1.4.1) as Mandalorion invokes it (reference utils/SpliceDefineConsensus.py:917;
+ * version pinned by reference setup.sh:17-19, Mando.py:257, README.md:79).
+ *
+ * TEST INFRASTRUCTURE ONLY (see mpoa_oracle.h).  PARITY UNPINNED: abPOA's source is a
+ * third-party dependency absent from /root/reference and from this image; every function
+ * below restates the published algorithm of the upstream file named in its comment
+ * (upstream paths are abPOA-v1.4.1/src/...), following SURVEY.md Appendix A.
+ *
+ * The restatement keeps abPOA's observable conventions, not its SIMD code:
+ *   - node 0 = source, node 1 = sink, edge arrays in first-creation order (A.3, A.8);
+ *   - BFS topological order with aligned-node groups enqueued together, max_remain via
+ *     reverse BFS over the heaviest out-edge (A.5);
+ *   - adaptive band rounded to whole SIMD vectors of `pn` lanes, clamped by the
+ *     predecessors' vector ranges; the diagonal is NOT carried across the first vector
+ *     of the overlap with a predecessor (an artefact of the shift-in of -inf) (A.5);
+ *   - convex-gap recurrences with abPOA's finite "-inf" and saturating int16 lanes (A.6);
+ *   - value-comparison traceback with the M > E1/E2 (per predecessor) > F1 > F2 priority
+ *     and the open/extend state machine (A.7);
+ *   - add-alignment with aligned-node cliques (A.8) and heaviest bundling (A.9).
+ */
+#include <algorithm>
+#include <atomic>
+#include <climits>
+#include <cstdint>
+#include <cstring>
+#include <deque>
+#include <thread>
+#include <vector>
+
+#include "mpoa_oracle.h"
+
+namespace {
+
+enum { OP_M = 1, OP_E1 = 2, OP_E2 = 4, OP_E = 6, OP_F1 = 8, OP_F2 = 16, OP_F = 24, OP_ALL = 31 };
+enum { SRC = 0, SINK = 1 };
+
+struct Par {
+    int m = 5;
+    int mat[25];
+    int match, mismatch;  // mismatch stored positive
+    int o1, e1, o2, e2, oe1, oe2;
+    int wb;
+    float wf;
+    int pn16, pn32;
+    mpoa_oracle_opts opt;
+};
+
+/* upstream abpoa_align.c: gen_simple_mat() -- N (code 4) scores 0 against everything (A.2) */
+void make_matrix(Par &P) {
+    for (int i = 0; i < 5; ++i)
+        for (int j = 0; j < 5; ++j)
+            P.mat[i * 5 + j] = (i == 4 || j == 4) ? 0 : (i == j ? P.match : -P.mismatch);
+}
+
+/* upstream abpoa_seq.c: ab_nt4_table -- ACGT (either case) -> 0..3, everything else 4 */
+inline uint8_t nt4(uint8_t c) {
+    switch (c) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': return 3;
+        default: return 4;
+    }
+}
+
+struct Node {
+    uint8_t base = 0;
+    int creator = -1;
+    std::vector<int> in_id, out_id, out_w, aligned;
+};
+
+struct Graph {
+    std::vector<Node> node;
+    bool sorted = false;
+    std::vector<int> index_to_node_id, node_id_to_index, max_remain, max_pos_left, max_pos_right;
+    Graph() { node.resize(2); }
+    int node_n() const { return (int)node.size(); }
+};
+
+/* upstream abpoa_graph.c: abpoa_add_graph_node() */
+int add_node(Graph &g, uint8_t base, int creator) {
+    g.node.emplace_back();
+    g.node.back().base = base;
+    g.node.back().creator = creator;
+    return g.node_n() - 1;
+}
+
+/* upstream abpoa_graph.c: abpoa_add_graph_edge(); check_edge=0 appends without search */
+void add_edge(Graph &g, int from, int to, int check_edge, int w) {
+    Node &f = g.node[from];
+    if (check_edge) {
+        for (size_t i = 0; i < f.out_id.size(); ++i)
+            if (f.out_id[i] == to) { f.out_w[i] += w; return; }
+    }
+    g.node[to].in_id.push_back(from);
+    f.out_id.push_back(to);
+    f.out_w.push_back(w);
+}
+
+/* upstream abpoa_graph.c: abpoa_add_graph_aligned_node() -- clique over the column (A.8) */
+void add_aligned(Graph &g, int node_id, int aligned_id) {
+    std::vector<int> sib = g.node[node_id].aligned;
+    for (int s : sib) {
+        g.node[s].aligned.push_back(aligned_id);
+        g.node[aligned_id].aligned.push_back(s);
+    }
+    g.node[node_id].aligned.push_back(aligned_id);
+    g.node[aligned_id].aligned.push_back(node_id);
+}
+
+/* upstream abpoa_graph.c: abpoa_get_aligned_id() */
+int get_aligned_id(const Graph &g, int node_id, uint8_t base) {
+    for (int a : g.node[node_id].aligned)
+        if (g.node[a].base == base) return a;
+    return -1;
+}
+
+/* upstream abpoa_graph.c: abpoa_BFS_set_node_index() (A.5) */
+bool bfs_set_node_index(Graph &g) {
+    int n = g.node_n();
+    std::vector<int> in_degree(n);
+    for (int i = 0; i < n; ++i) in_degree[i] = (int)g.node[i].in_id.size();
+    std::deque<int> q;
+    q.push_back(SRC);
+    int index = 0;
+    while (!q.empty()) {
+        int cur = q.front();
+        q.pop_front();
+        g.index_to_node_id[index] = cur;
+        g.node_id_to_index[cur] = index++;
+        if (cur == SINK) return true;
+        for (int out_id : g.node[cur].out_id) {
+            if (--in_degree[out_id] == 0) {
+                bool ready = true;
+                for (int a : g.node[out_id].aligned)
+                    if (in_degree[a] != 0) { ready = false; break; }
+                if (!ready) continue;
+                q.push_back(out_id);
+                for (int a : g.node[out_id].aligned) q.push_back(a);
+            }
+        }
+    }
+    return false;  // abPOA: err_fatal("Failed to set node index")
+}
+
+/* upstream abpoa_graph.c: abpoa_BFS_set_node_remain() (A.5) */
+bool bfs_set_node_remain(Graph &g) {
+    int n = g.node_n();
+    std::vector<int> out_degree(n);
+    for (int i = 0; i < n; ++i) {
+        out_degree[i] = (int)g.node[i].out_id.size();
+        g.max_remain[i] = 0;
+    }
+    std::deque<int> q;
+    q.push_back(SINK);
+    g.max_remain[SINK] = -1;
+    while (!q.empty()) {
+        int cur = q.front();
+        q.pop_front();
+        if (cur != SINK) {
+            int max_w = -1, max_id = -1;
+            const Node &nd = g.node[cur];
+            for (size_t i = 0; i < nd.out_id.size(); ++i)
+                if (nd.out_w[i] > max_w) { max_w = nd.out_w[i]; max_id = nd.out_id[i]; }
+            g.max_remain[cur] = g.max_remain[max_id] + 1;
+        }
+        if (cur == SRC) return true;
+        for (int in_id : g.node[cur].in_id)
+            if (--out_degree[in_id] == 0) q.push_back(in_id);
+    }
+    return false;
+}
+
+/* upstream abpoa_graph.c: abpoa_topological_sort() */
+bool topological_sort(Graph &g) {
+    int n = g.node_n();
+    g.index_to_node_id.assign(n, 0);
+    g.node_id_to_index.assign(n, 0);
+    g.max_remain.assign(n, 0);
+    if (!bfs_set_node_index(g)) return false;
+    g.max_pos_right.assign(n, 0);
+    g.max_pos_left.assign(n, n);
+    if (!bfs_set_node_remain(g)) return false;
+    g.sorted = true;
+    return true;
+}
+
+struct Cig { int op; int node_id; int qidx; };  // op: 0 match, 1 ins, 2 del
+
+struct AlnOut {
+    std::vector<Cig> cigar;  // forward order
+    int best_score = 0;
+    int bits = 0;
+    int64_t band_cells = 0, int_ops = 0, full_cells = 0;
+    bool ok = false;
+};
+
+struct DpScratch {
+    std::vector<int> dp_beg, dp_end, dp_beg_sn, dp_end_sn, cell_hi;
+    std::vector<int64_t> off;
+    std::vector<int32_t> H, E1, E2, F1, F2;
+    std::vector<int> pre_off, pre_idx;
+    std::vector<int32_t> mx, ei1, ei2;
+};
+
+inline int32_t sat(int64_t x, int32_t lo) { return x < lo ? lo : (int32_t)x; }
+
+/*
+ * upstream simd_abpoa_align.c: simd_abpoa_align_sequence_to_subgraph() with
+ * abpoa_cg_global_align_sequence_to_graph_core (first row, per-row DP, best cell,
+ * cg backtrack) for the whole graph in global mode, adaptive band on.
+ */
+void align_to_graph(Graph &g, const Par &P, const uint8_t *q, int qlen, DpScratch &S, AlnOut &R) {
+    R.ok = false;
+    R.cigar.clear();
+    const int gn = g.node_n();
+    /* lane width decision (A.4) */
+    const int len = qlen > gn ? qlen : gn;
+    const int64_t max_score = std::max<int64_t>((int64_t)qlen * P.match, (int64_t)len * P.e1 + P.o1);
+    const bool is16 = max_score <= INT16_MAX - P.mismatch - P.o1 - P.e1 - P.o2 - P.e2;
+    const int pn = is16 ? P.pn16 : P.pn32;
+    const int32_t type_min = is16 ? INT16_MIN : INT32_MIN;
+    const int32_t inf_min = (int32_t)(std::max({(int64_t)type_min + P.mismatch, (int64_t)type_min + P.oe1,
+                                                (int64_t)type_min + P.oe2}) +
+                                      31 * std::max(P.e1, P.e2));
+    R.bits = is16 ? 16 : 32;
+    const int w = P.wb < 0 ? qlen : P.wb + (int)(P.wf * (float)qlen);  // float product, as in C
+
+    /* predecessor rows in in_id order */
+    S.pre_off.assign(gn + 1, 0);
+    S.pre_idx.clear();
+    for (int i = 0; i < gn; ++i) {
+        const Node &nd = g.node[g.index_to_node_id[i]];
+        S.pre_off[i] = (int)S.pre_idx.size();
+        for (int in_id : nd.in_id) S.pre_idx.push_back(g.node_id_to_index[in_id]);
+    }
+    S.pre_off[gn] = (int)S.pre_idx.size();
+
+    S.dp_beg.assign(gn, 0); S.dp_end.assign(gn, -1); S.dp_beg_sn.assign(gn, 0); S.dp_end_sn.assign(gn, -1);
+    S.cell_hi.assign(gn, -1);
+    S.off.assign(gn, 0);
+    S.H.clear(); S.E1.clear(); S.E2.clear(); S.F1.clear(); S.F2.clear();
+
+    auto band_beg = [&](int node_id) {
+        return std::max(0, std::min(g.max_pos_left[node_id], qlen - g.max_remain[node_id]) - w);
+    };
+    auto band_end = [&](int node_id) {
+        return std::min(qlen, std::max(g.max_pos_right[node_id], qlen - g.max_remain[node_id]) + w);
+    };
+
+    /* first row (source) */
+    {
+        g.max_pos_left[SRC] = g.max_pos_right[SRC] = 0;
+        for (int out_id : g.node[SRC].out_id) g.max_pos_left[out_id] = g.max_pos_right[out_id] = 1;
+        int b = band_beg(SRC), e = band_end(SRC);
+        S.dp_beg_sn[0] = b / pn; S.dp_end_sn[0] = e / pn;
+        S.dp_beg[0] = S.dp_beg_sn[0] * pn; S.dp_end[0] = (S.dp_end_sn[0] + 1) * pn - 1;
+        int hi = std::min(S.dp_end[0], qlen);
+        S.cell_hi[0] = hi;
+        S.off[0] = 0;
+        int width = hi - S.dp_beg[0] + 1;
+        S.H.assign(width, inf_min); S.E1.assign(width, inf_min); S.E2.assign(width, inf_min);
+        S.F1.assign(width, inf_min); S.F2.assign(width, inf_min);
+        // dp_beg[0] is 0 by construction
+        S.H[0] = 0; S.E1[0] = -P.oe1; S.E2[0] = -P.oe2;
+        for (int i = 1; i <= hi; ++i) {
+            S.F1[i] = -(P.o1 + P.e1 * i);
+            S.F2[i] = -(P.o2 + P.e2 * i);
+            S.H[i] = std::max(S.F1[i], S.F2[i]);
+        }
+    }
+
+    /* rows 1 .. gn-2 (the sink row is never computed) */
+    for (int index_i = 1; index_i < gn - 1; ++index_i) {
+        const int node_id = g.index_to_node_id[index_i];
+        const int *pre = &S.pre_idx[S.pre_off[index_i]];
+        const int npre = S.pre_off[index_i + 1] - S.pre_off[index_i];
+        int beg = band_beg(node_id), end = band_end(node_id);
+        int beg_sn = beg / pn, end_sn = end / pn;
+        int min_pre_beg_sn = INT_MAX, max_pre_end_sn = -1;
+        for (int k = 0; k < npre; ++k) {
+            min_pre_beg_sn = std::min(min_pre_beg_sn, S.dp_beg_sn[pre[k]]);
+            max_pre_end_sn = std::max(max_pre_end_sn, S.dp_end_sn[pre[k]]);
+        }
+        if (beg_sn < min_pre_beg_sn) beg_sn = min_pre_beg_sn;
+        if (P.opt.clamp_end_to_pred && end_sn > max_pre_end_sn + 1) end_sn = max_pre_end_sn + 1;
+        S.dp_beg_sn[index_i] = beg_sn; S.dp_end_sn[index_i] = end_sn;
+        const int dp_beg = S.dp_beg[index_i] = beg_sn * pn;
+        const int dp_end = S.dp_end[index_i] = (end_sn + 1) * pn - 1;
+        const int hi_cell = std::min(dp_end, qlen);
+        S.cell_hi[index_i] = hi_cell;
+        const int width = std::max(0, hi_cell - dp_beg + 1);
+        const int64_t off = (int64_t)S.H.size();
+        S.off[index_i] = off;
+        S.H.resize(off + width); S.E1.resize(off + width); S.E2.resize(off + width);
+        S.F1.resize(off + width); S.F2.resize(off + width);
+        R.band_cells += width;
+        R.int_ops += 17LL * width + 3LL * std::max(0, npre - 1) * width;
+        R.full_cells += qlen + 1;
+
+        int max = inf_min, left_max_i = -1, right_max_i = -1;
+        if (width > 0) {
+            S.mx.assign(width, inf_min); S.ei1.assign(width, inf_min); S.ei2.assign(width, inf_min);
+            for (int k = 0; k < npre; ++k) {
+                const int p = pre[k];
+                const int lo = std::max(beg_sn, S.dp_beg_sn[p]) * pn;
+                const int hi = std::min((std::min(end_sn, S.dp_end_sn[p]) + 1) * pn - 1, qlen);
+                const int32_t *Hp = &S.H[S.off[p]] - S.dp_beg[p];
+                const int32_t *E1p = &S.E1[S.off[p]] - S.dp_beg[p];
+                const int32_t *E2p = &S.E2[S.off[p]] - S.dp_beg[p];
+                for (int j = lo; j <= hi; ++j) {
+                    const int32_t mv = (j == lo) ? inf_min : Hp[j - 1];
+                    const int c = j - dp_beg;
+                    S.mx[c] = std::max(S.mx[c], mv);
+                    S.ei1[c] = std::max(S.ei1[c], E1p[j]);
+                    S.ei2[c] = std::max(S.ei2[c], E2p[j]);
+                }
+            }
+            const int *mrow = &P.mat[g.node[node_id].base * 5];
+            int32_t *Hr = &S.H[off], *E1r = &S.E1[off], *E2r = &S.E2[off], *F1r = &S.F1[off], *F2r = &S.F2[off];
+            int32_t hh_prev = inf_min, f1 = inf_min, f2 = inf_min;
+            for (int c = 0; c < width; ++c) {
+                const int j = dp_beg + c;
+                const int s = j > 0 ? mrow[q[j - 1]] : 0;
+                int32_t hh = sat((int64_t)S.mx[c] + s, type_min);
+                hh = std::max(hh, std::max(S.ei1[c], S.ei2[c]));
+                if (c == 0) {
+                    f1 = sat((int64_t)inf_min - P.oe1, type_min);
+                    f2 = sat((int64_t)inf_min - P.oe2, type_min);
+                } else {
+                    f1 = std::max(sat((int64_t)hh_prev - P.oe1, type_min), sat((int64_t)f1 - P.e1, type_min));
+                    f2 = std::max(sat((int64_t)hh_prev - P.oe2, type_min), sat((int64_t)f2 - P.e2, type_min));
+                }
+                hh_prev = hh;
+                const int32_t h = std::max(hh, std::max(f1, f2));
+                Hr[c] = h; F1r[c] = f1; F2r[c] = f2;
+                E1r[c] = std::max(sat((int64_t)S.ei1[c] - P.e1, type_min), sat((int64_t)h - P.oe1, type_min));
+                E2r[c] = std::max(sat((int64_t)S.ei2[c] - P.e2, type_min), sat((int64_t)h - P.oe2, type_min));
+                if (h > max) { max = h; left_max_i = right_max_i = j; }
+                else if (h == max && !P.opt.single_argmax) right_max_i = j;
+            }
+        }
+        for (int out_id : g.node[node_id].out_id) {
+            if (right_max_i + 1 > g.max_pos_right[out_id]) g.max_pos_right[out_id] = right_max_i + 1;
+            if (left_max_i + 1 < g.max_pos_left[out_id]) g.max_pos_left[out_id] = left_max_i + 1;
+        }
+    }
+
+    /* best end cell: sink's in-neighbours in in_id order, strictly greater wins (A.6) */
+    auto in_band = [&](int row, int j) { return j >= S.dp_beg[row] && j <= S.cell_hi[row]; };
+    auto val = [&](const std::vector<int32_t> &A, int row, int j) -> int32_t {
+        return in_band(row, j) ? A[S.off[row] + (j - S.dp_beg[row])] : inf_min;
+    };
+    int best_score = inf_min, best_i = 0, best_j = 0;
+    for (int in_id : g.node[SINK].in_id) {
+        const int in_index = g.node_id_to_index[in_id];
+        const int end = std::min(qlen, S.dp_end[in_index]);
+        const int32_t v = val(S.H, in_index, end);
+        if (v > best_score) { best_score = v; best_i = in_index; best_j = end; }
+    }
+    R.best_score = best_score;
+
+    /* cg backtrack (A.7) */
+    std::vector<Cig> rev;
+    int i = best_i, j = best_j, cur_op = OP_ALL;
+    if (best_j < qlen)
+        for (int t = qlen - 1; t >= best_j; --t) rev.push_back({1, -1, t});
+    while (i > 0 && j > 0) {
+        const int id = g.index_to_node_id[i];
+        const int *pre = &S.pre_idx[S.pre_off[i]];
+        const int npre = S.pre_off[i + 1] - S.pre_off[i];
+        const int s = P.mat[g.node[id].base * 5 + q[j - 1]];
+        const int32_t hij = val(S.H, i, j);
+        bool hit = false;
+        if (cur_op & OP_M) {
+            for (int k = 0; k < npre; ++k) {
+                const int p = pre[k];
+                if (j - 1 < S.dp_beg[p] || j - 1 > S.dp_end[p]) continue;
+                if ((int64_t)val(S.H, p, j - 1) + s == hij) {
+                    rev.push_back({0, id, j - 1});
+                    i = p; --j; hit = true; cur_op = OP_ALL;
+                    break;
+                }
+            }
+        }
+        if (!hit && (cur_op & OP_E)) {
+            for (int k = 0; k < npre && !hit; ++k) {
+                const int p = pre[k];
+                if (j < S.dp_beg[p] || j > S.dp_end[p]) continue;
+                if (cur_op & OP_E1) {
+                    const int32_t pe1 = val(S.E1, p, j);
+                    const bool take = (cur_op & OP_M) ? (hij == pe1)
+                                                      : ((int64_t)val(S.E1, i, j) == (int64_t)pe1 - P.e1);
+                    if (take) {
+                        cur_op = ((int64_t)val(S.H, p, j) - P.oe1 == pe1) ? (OP_M | OP_F) : OP_E1;
+                        rev.push_back({2, id, j - 1});
+                        i = p; hit = true;
+                        break;
+                    }
+                }
+                if (cur_op & OP_E2) {
+                    const int32_t pe2 = val(S.E2, p, j);
+                    const bool take = (cur_op & OP_M) ? (hij == pe2)
+                                                      : ((int64_t)val(S.E2, i, j) == (int64_t)pe2 - P.e2);
+                    if (take) {
+                        cur_op = ((int64_t)val(S.H, p, j) - P.oe2 == pe2) ? (OP_M | OP_F) : OP_E2;
+                        rev.push_back({2, id, j - 1});
+                        i = p; hit = true;
+                        break;
+                    }
+                }
+            }
+        }
+        if (!hit && (cur_op & OP_F)) {
+            if (cur_op & OP_F1) {
+                const int32_t f1 = val(S.F1, i, j);
+                if (!(cur_op & OP_M) || hij == f1) {
+                    if ((int64_t)val(S.H, i, j - 1) - P.oe1 == f1) { cur_op = OP_M | OP_E; hit = true; }
+                    else if ((int64_t)val(S.F1, i, j - 1) - P.e1 == f1) { cur_op = OP_F1; hit = true; }
+                }
+            }
+            if (!hit && (cur_op & OP_F2)) {
+                const int32_t f2 = val(S.F2, i, j);
+                if (!(cur_op & OP_M) || hij == f2) {
+                    if ((int64_t)val(S.H, i, j - 1) - P.oe2 == f2) { cur_op = OP_M | OP_E; hit = true; }
+                    else if ((int64_t)val(S.F2, i, j - 1) - P.e2 == f2) { cur_op = OP_F2; hit = true; }
+                }
+            }
+            if (hit) { rev.push_back({1, id, j - 1}); --j; }
+        }
+        if (!hit) return;  // abPOA: err_fatal("Error in cg_backtrack") -> process dies, no output
+    }
+    for (int t = j - 1; t >= 0; --t) rev.push_back({1, -1, t});
+    R.cigar.assign(rev.rbegin(), rev.rend());
+    R.ok = true;
+}
+
+/* upstream abpoa_graph.c: abpoa_add_graph_sequence() -- first read, linear chain (A.3) */
+void add_sequence(Graph &g, const uint8_t *seq, int len, int creator0, int32_t *base_aln, int32_t *base_node) {
+    int last = SRC;
+    for (int i = 0; i < len; ++i) {
+        int cur = add_node(g, seq[i], creator0 + i);
+        add_edge(g, last, cur, 0, 1);
+        last = cur;
+        if (base_aln) base_aln[i] = -1;
+        if (base_node) base_node[i] = creator0 + i;
+    }
+    add_edge(g, last, SINK, 0, 1);
+    g.sorted = false;
+}
+
+/* upstream abpoa_graph.c: abpoa_add_subgraph_alignment() over the whole graph (A.8) */
+void add_alignment(Graph &g, const uint8_t *seq, int len, const std::vector<Cig> &cigar, int creator0,
+                   int32_t *base_aln, int32_t *base_node) {
+    int last_id = SRC, last_new = 0, query_id = -1;
+    for (const Cig &c : cigar) {
+        if (c.op == 0) {
+            ++query_id;
+            const int node_id = c.node_id;
+            if (base_aln) base_aln[query_id] = g.node[node_id].creator;
+            if (g.node[node_id].base != seq[query_id]) {
+                int aligned_id = get_aligned_id(g, node_id, seq[query_id]);
+                if (aligned_id != -1) {
+                    add_edge(g, last_id, aligned_id, 1 - last_new, 1);
+                    last_id = aligned_id; last_new = 0;
+                } else {
+                    int new_id = add_node(g, seq[query_id], creator0 + query_id);
+                    add_edge(g, last_id, new_id, 0, 1);
+                    last_id = new_id; last_new = 1;
+                    add_aligned(g, node_id, new_id);
+                }
+            } else {
+                add_edge(g, last_id, node_id, 1 - last_new, 1);
+                last_id = node_id; last_new = 0;
+            }
+            if (base_node) base_node[query_id] = g.node[last_id].creator;
+        } else if (c.op == 1) {
+            ++query_id;
+            int new_id = add_node(g, seq[query_id], creator0 + query_id);
+            add_edge(g, last_id, new_id, 0, 1);
+            last_id = new_id; last_new = 1;
+            if (base_aln) base_aln[query_id] = -1;
+            if (base_node) base_node[query_id] = creator0 + query_id;
+        }
+    }
+    (void)len;
+    add_edge(g, last_id, SINK, 1 - last_new, 1);
+    g.sorted = false;
+}
+
+/* upstream abpoa_output.c: abpoa_heaviest_bundling() + abpoa_set_hb_cons(), n_clu = 1 (A.9) */
+bool heaviest_bundling(const Graph &g, const Par &P, std::vector<uint8_t> &cons) {
+    const int n = g.node_n();
+    std::vector<int> out_degree(n), score(n, 0), max_out_id(n, -1);
+    for (int i = 0; i < n; ++i) out_degree[i] = (int)g.node[i].out_id.size();
+    std::deque<int> q;
+    q.push_back(SINK);
+    bool done = false;
+    while (!q.empty()) {
+        int cur = q.front();
+        q.pop_front();
+        const Node &nd = g.node[cur];
+        if (cur == SINK) {
+            max_out_id[cur] = -1; score[cur] = 0;
+        } else if (cur == SRC) {
+            int path_score = -1, path_max_w = -1, max_id = -1;
+            for (size_t i = 0; i < nd.out_id.size(); ++i) {
+                int out_id = nd.out_id[i], out_w = nd.out_w[i];
+                if (out_w > path_max_w || (out_w == path_max_w && score[out_id] > path_score)) {
+                    max_id = out_id; path_score = score[out_id]; path_max_w = out_w;
+                }
+            }
+            max_out_id[cur] = max_id;
+        } else {
+            int max_w = INT_MIN, max_id = -1;
+            for (size_t i = 0; i < nd.out_id.size(); ++i) {
+                int out_id = nd.out_id[i], out_w = nd.out_w[i];
+                if (max_w < out_w) { max_w = out_w; max_id = out_id; }
+                else if (max_w == out_w) {
+                    if (P.opt.hb_tie_later_wins ? (score[max_id] <= score[out_id]) : (score[max_id] < score[out_id]))
+                        max_id = out_id;
+                }
+            }
+            score[cur] = max_w + score[max_id];
+            max_out_id[cur] = max_id;
+        }
+        if (cur == SRC) { done = true; break; }
+        for (int in_id : nd.in_id)
+            if (--out_degree[in_id] == 0) q.push_back(in_id);
+    }
+    if (!done) return false;
+    cons.clear();
+    int cur = max_out_id[SRC];
+    while (cur != SINK && cur >= 0) {
+        cons.push_back("ACGTN"[g.node[cur].base]);
+        cur = max_out_id[cur];
+    }
+    return cur == SINK;
+}
+
+struct GroupOut {
+    std::vector<uint8_t> cons;
+    int status = MPOA_GROUP_EMPTY;
+    mpoa_stats st;
+};
+
+/* upstream abpoa.c: abpoa_msa1() -> abpoa_poa() -> abpoa_output(), seeding disabled */
+void run_group(const Par &P, int64_t r0, int64_t r1, const int64_t *read_base_off, const uint8_t *bases,
+               mpoa_trace *tr, GroupOut &out) {
+    std::memset(&out.st, 0, sizeof(out.st));
+    out.st.n_groups = 1;
+    out.st.n_reads = r1 - r0;
+    out.status = MPOA_GROUP_EMPTY;
+    out.cons.clear();
+    if (r1 <= r0) return;
+    Graph g;
+    DpScratch S;
+    AlnOut R;
+    std::vector<uint8_t> seq;
+    const int64_t gbase = read_base_off[r0];
+    for (int64_t r = r0; r < r1; ++r) {
+        const int64_t b0 = read_base_off[r], b1 = read_base_off[r + 1];
+        const int len = (int)(b1 - b0);
+        seq.resize(len);
+        for (int i = 0; i < len; ++i) seq[i] = nt4(bases[b0 + i]);
+        int32_t *baln = tr && tr->base_aln ? tr->base_aln + b0 : nullptr;
+        int32_t *bnode = tr && tr->base_node ? tr->base_node + b0 : nullptr;
+        if (tr && tr->read_score) tr->read_score[r] = 0;
+        if (tr && tr->read_bits) tr->read_bits[r] = 0;
+        if (tr && tr->read_band_cells) tr->read_band_cells[r] = 0;
+        if (g.node_n() == 2) {
+            /* abpoa_add_graph_sequence dies on an empty first read -> no output at all */
+            if (len <= 0) return;
+            add_sequence(g, seq.data(), len, (int)(b0 - gbase), baln, bnode);
+            continue;
+        }
+        if (len <= 0) continue;  // abpoa_align_sequence_to_graph returns early, nothing is added
+        if (!g.sorted && !topological_sort(g)) return;
+        R.band_cells = R.int_ops = R.full_cells = 0;
+        align_to_graph(g, P, seq.data(), len, S, R);
+        out.st.n_alignments++;
+        out.st.band_cells += R.band_cells;
+        out.st.int_ops += R.int_ops;
+        out.st.full_cells += R.full_cells;
+        (R.bits == 16 ? out.st.n_align_i16 : out.st.n_align_i32)++;
+        if (tr && tr->read_score) tr->read_score[r] = R.best_score;
+        if (tr && tr->read_bits) tr->read_bits[r] = R.bits;
+        if (tr && tr->read_band_cells) tr->read_band_cells[r] = R.band_cells;
+        if (!R.ok) return;  // abpoa exits -> empty consensus file -> reference falls back
+        add_alignment(g, seq.data(), len, R.cigar, (int)(b0 - gbase), baln, bnode);
+    }
+    if (g.node_n() <= 2) return;
+    if (heaviest_bundling(g, P, out.cons)) out.status = MPOA_GROUP_OK;
+    else out.cons.clear();
+}
+
+void add_stats(mpoa_stats &a, const mpoa_stats &b) {
+    a.n_groups += b.n_groups; a.n_reads += b.n_reads; a.n_alignments += b.n_alignments;
+    a.band_cells += b.band_cells; a.full_cells += b.full_cells; a.int_ops += b.int_ops;
+    a.n_align_i16 += b.n_align_i16; a.n_align_i32 += b.n_align_i32;
+}
+
+}  // namespace
+
+extern "C" void mpoa_oracle_default_opts(mpoa_oracle_opts *o) {
+    std::memset(o, 0, sizeof(*o));
+    o->clamp_end_to_pred = 1;
+    o->single_argmax = 0;
+    o->hb_tie_later_wins = 1;
+    o->n_threads = 1;
+}
+
+extern "C" int mpoa_oracle_consensus_batch(const mpoa_params *p, const mpoa_oracle_opts *o, int64_t n_groups,
+                                           const int64_t *group_read_off, const int64_t *read_base_off,
+                                           const uint8_t *bases, const uint8_t *group_flags, int64_t *cons_off,
+                                           uint8_t *cons_buf, int64_t cons_cap, int32_t *group_status,
+                                           mpoa_stats *stats, mpoa_trace *trace) {
+    (void)group_flags;  // -S (seeding) is not restated: the unseeded path is run for every group
+    if (!p || n_groups < 0 || (n_groups > 0 && (!group_read_off || !read_base_off || !cons_off))) return MPOA_EINVAL;
+    Par P;
+    P.match = p->match < 0 ? -p->match : p->match;
+    P.mismatch = p->mismatch < 0 ? -p->mismatch : p->mismatch;
+    P.o1 = p->gap_open1; P.e1 = p->gap_ext1; P.o2 = p->gap_open2; P.e2 = p->gap_ext2;
+    P.oe1 = P.o1 + P.e1; P.oe2 = P.o2 + P.e2;
+    P.wb = p->wb; P.wf = p->wf;
+    P.pn16 = p->simd_pn_i16 > 0 ? p->simd_pn_i16 : 16;
+    P.pn32 = p->simd_pn_i32 > 0 ? p->simd_pn_i32 : 8;
+    if (o) P.opt = *o; else mpoa_oracle_default_opts(&P.opt);
+    make_matrix(P);
+
+    std::vector<GroupOut> outs((size_t)n_groups);
+    int nt = std::max(1, P.opt.n_threads);
+    if (nt > n_groups) nt = (int)std::max<int64_t>(1, n_groups);
+    std::atomic<int64_t> next(0);
+    auto worker = [&]() {
+        for (;;) {
+            int64_t gidx = next.fetch_add(1);
+            if (gidx >= n_groups) break;
+            run_group(P, group_read_off[gidx], group_read_off[gidx + 1], read_base_off, bases, trace, outs[gidx]);
+        }
+    };
+    if (nt <= 1) worker();
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(worker);
+        for (auto &t : th) t.join();
+    }
+    mpoa_stats tot;
+    std::memset(&tot, 0, sizeof(tot));
+    int64_t pos = 0;
+    bool overflow = false;
+    for (int64_t gidx = 0; gidx < n_groups; ++gidx) {
+        cons_off[gidx] = pos;
+        const auto &c = outs[gidx].cons;
+        if (!overflow && pos + (int64_t)c.size() <= cons_cap && cons_buf) std::memcpy(cons_buf + pos, c.data(), c.size());
+        else if (!c.empty()) overflow = true;
+        pos += (int64_t)c.size();
+        if (group_status) group_status[gidx] = outs[gidx].status;
+        add_stats(tot, outs[gidx].st);
+    }
+    cons_off[n_groups] = pos;
+    if (stats) *stats = tot;
+    return overflow ? MPOA_ENOSPC : MPOA_OK;
+}
