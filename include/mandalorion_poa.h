@@ -84,7 +84,9 @@ typedef struct mpoa_stats {
     double  h2d_ms;          /* host->device copies (0 for the *_device entry point)     */
     double  d2h_ms;          /* device->host copies                                      */
     int64_t n_kernel_launches; /* kernels of this library launched by the call           */
-    int64_t reserved[4];
+    int64_t phase_cycles[6];  /* SM cycles summed over warps: graph-prep, DP, traceback,
+                                 merge, consensus, total busy                            */
+    int64_t reserved[2];
 } mpoa_stats;
 
 /*

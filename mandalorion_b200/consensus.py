@@ -1,0 +1,239 @@
+"""Host-side mirror of the reference's consensus step, batched for the GPU.
+
+Reference interface mirrored here (same names, argument meaning and fall-backs):
+
+  determine_consensus(reads, root, abpoa) -> (consensus, names)
+        utils/SpliceDefineConsensus.py:876-931
+  the per-locus loop that calls it                    defineIsoforms.py:87-91
+  the writer of Isoform_Consensi.fasta / reads2isoforms.txt   defineIsoforms.py:155-166
+
+What changes structurally: the reference runs one `abpoa` process per isoform inside forked
+workers; the GPU wants thousands of groups per call.  So the step is split in two:
+
+  prepare_group()   everything determine_consensus() does BEFORE abpoa (lines :878-:915):
+                    the np.random.choice subsample/permutation (same call, same RNG
+                    consumption), orientation of every read against the first one, the
+                    "<= 2 usable reads" bypass and the -S decision.  Returns a PendingGroup.
+  ConsensusBatcher  collects PendingGroups, runs them through PoaContext.consensus_batch()
+                    (the C ABI, CUDA) and applies the reference's post-processing
+                    (:921-:925: empty consensus -> first read).
+
+determine_consensus() below is the one-group convenience with the reference's signature.
+Nothing in this module computes an alignment on the CPU.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .poa import PoaContext, pack_groups
+
+_COMP = bytes.maketrans(b"ACGTUNacgtun", b"TGCAANtgcaan")
+
+
+def revcomp(seq: str) -> str:
+    """mappy.revcomp equivalent (reference :905)."""
+    return seq.encode().translate(_COMP)[::-1].decode()
+
+
+# ------------------------------------------------------------------------------------------
+# orientation (reference :895, :900-907 -- mappy `map-ont` of every read against read 0)
+# ------------------------------------------------------------------------------------------
+
+class MappyOrienter:
+    """Exactly the reference's calls; used whenever mappy is importable."""
+
+    def __init__(self, first):
+        import mappy as mp
+        self._mp = mp
+        self._al = mp.Aligner(seq=first, preset="map-ont")
+
+    def hits(self, sequence):
+        """Strands of the primary hits, in mappy's order (a read may have 0, 1 or 2)."""
+        return [h.strand for h in self._al.map(sequence) if h.is_primary]
+
+
+class KmerOrienter:
+    """Stand-in when mappy is absent (it is not installable in the build image): a k-mer strand
+    vote against the first read.  One 'primary hit' on the winning strand, none when neither
+    strand shares enough k-mers (the reference drops such reads, :902-907).  This is NOT
+    minimap2; it reproduces its strand call for reads of one isoform.  SURVEY.md section 8f
+    ranks the exact orientation step as the next row to build."""
+
+    K = 13
+
+    def __init__(self, first):
+        self._set = self._kmers(first)
+
+    @classmethod
+    def _kmers(cls, s):
+        k = cls.K
+        return {s[i:i + k] for i in range(0, max(0, len(s) - k + 1))}
+
+    def _score(self, s):
+        k = self.K
+        st = self._set
+        return sum(1 for i in range(0, max(0, len(s) - k + 1), 3) if s[i:i + k] in st)
+
+    def hits(self, sequence):
+        f = self._score(sequence)
+        r = self._score(revcomp(sequence))
+        need = max(2, (len(sequence) // 3) // 50)
+        if max(f, r) < need:
+            return []
+        return [1 if f >= r else -1]
+
+
+def default_orienter(first):
+    try:
+        return MappyOrienter(first)
+    except ImportError:
+        return KmerOrienter(first)
+
+
+# ------------------------------------------------------------------------------------------
+# prepare: determine_consensus() up to the abpoa call
+# ------------------------------------------------------------------------------------------
+
+@dataclass
+class PendingGroup:
+    names: list                    # ALL read names of the isoform (reference :880-882, :931)
+    sequences: list                # oriented reads in abpoa's file order (reference :906-907)
+    seq_lengths: list              # lengths of every subsampled read, dropped ones included (:901)
+    bypass: bool                   # len(sequences) <= 2 -> consensus = sequences[0] (:911-912)
+    seed: bool                     # median length >= 8000 -> the reference adds -S (:915-919)
+    tag: object = None
+    consensus: str = field(default=None)
+
+
+def prepare_group(reads, orienter_factory=default_orienter, rng=None, tag=None):
+    """reads: [(name, seq), ...] exactly as define_start_end_sites() yields them.
+
+    Consumes the NumPy RNG exactly like the reference: one
+    np.random.choice(np.arange(0, n), min(n, 100), replace=False) on the GLOBAL legacy RNG
+    (or on `rng` when a RandomState is passed, for tests)."""
+    fasta_reads = []
+    names = []
+    for read, seq in reads:
+        fasta_reads.append((read, seq))
+        names.append(read)
+    choice = (rng or np.random).choice
+    indeces = choice(np.arange(0, len(fasta_reads)), min(len(fasta_reads), 100), replace=False)
+    subsample_fasta_reads = [fasta_reads[index] for index in indeces]
+    first = subsample_fasta_reads[0][1]
+    sequences = []
+    seq_lengths = []
+    orienter = orienter_factory(first)
+    for read, sequence in subsample_fasta_reads:
+        seq_lengths.append(len(sequence))
+        # the reference loop re-reverses `sequence` in place for every '-' primary hit
+        for strand in orienter.hits(sequence):
+            if strand == -1:
+                sequence = revcomp(sequence)
+            sequences.append(sequence)
+    bypass = len(sequences) <= 2
+    seed = (not bypass) and float(np.median(seq_lengths)) >= 8000
+    pg = PendingGroup(names=names, sequences=sequences, seq_lengths=seq_lengths, bypass=bypass, seed=seed, tag=tag)
+    if bypass:
+        # reference :912 -- IndexError when nothing mapped, like the reference
+        pg.consensus = sequences[0]
+    return pg
+
+
+class ConsensusBatcher:
+    """Collects pending groups and runs them in one GPU call; order of results == order of add()."""
+
+    def __init__(self, ctx: PoaContext = None, device=0, max_bases=1 << 30):
+        self._ctx = ctx
+        self._device = device
+        self._pending = []
+        self._max_bases = max_bases
+        self.stats = []
+
+    @property
+    def ctx(self):
+        if self._ctx is None:
+            self._ctx = PoaContext(self._device)   # raises PoaError without the CUDA library / GPU
+        return self._ctx
+
+    def add(self, pg: PendingGroup):
+        self._pending.append(pg)
+        return pg
+
+    def flush(self):
+        """Runs every non-bypassed pending group; fills .consensus; returns the groups in add() order."""
+        todo = [pg for pg in self._pending if not pg.bypass and pg.consensus is None]
+        start = 0
+        while start < len(todo):
+            nb, end = 0, start
+            while end < len(todo) and (end == start or nb + sum(map(len, todo[end].sequences)) <= self._max_bases):
+                nb += sum(map(len, todo[end].sequences))
+                end += 1
+            chunk = todo[start:end]
+            gro, rbo, bases = pack_groups([pg.sequences for pg in chunk])
+            flags = np.array([1 if pg.seed else 0 for pg in chunk], dtype=np.uint8)
+            ctx = self.ctx
+            ctx.upload(gro, rbo, bases, flags)
+            self.stats.append(ctx.run())
+            out = ctx.fetch()
+            for pg, cons, status in zip(chunk, out["cons"], out["status"]):
+                consensus_sequence = cons.decode() if status == 0 else ""
+                if not consensus_sequence:                    # reference :924-925
+                    consensus_sequence = pg.sequences[0]
+                pg.consensus = consensus_sequence
+            start = end
+        done, self._pending = self._pending, []
+        return done
+
+
+def determine_consensus(reads, root=None, abpoa=None, ctx=None, orienter_factory=default_orienter, rng=None):
+    """Drop-in for utils/SpliceDefineConsensus.determine_consensus (reference :876-931).
+
+    `root` (temp-file prefix) and `abpoa` (binary path) are accepted for signature
+    compatibility and unused: no file is written and no process is spawned."""
+    pg = prepare_group(reads, orienter_factory=orienter_factory, rng=rng)
+    if not pg.bypass:
+        b = ConsensusBatcher(ctx)
+        b.add(pg)
+        b.flush()
+    return pg.consensus, pg.names
+
+
+# ------------------------------------------------------------------------------------------
+# module-D dispatch (reference defineIsoforms.py:87-91 and :155-166)
+# ------------------------------------------------------------------------------------------
+
+def consensus_for_loci(loci_seqdicts, ctx=None, orienter_factory=default_orienter, rng=None):
+    """loci_seqdicts: iterable of (root, seqDict) in the reference's locus order, seqDict being
+    what define_start_end_sites() returned for that locus.  Returns {root: IsoData} with
+    IsoData[isoform] = [consensus, names] -- the structure process_locus() returns.
+
+    Groups are prepared in the reference's order (locus order, then dict order), so a
+    seeded global NumPy RNG is consumed identically, then ALL loci go to the GPU in one batch."""
+    batcher = ConsensusBatcher(ctx)
+    results = {}
+    for root, seq_dict in loci_seqdicts:
+        iso = {}
+        for isoform, reads in seq_dict.items():
+            pg = batcher.add(prepare_group(reads, orienter_factory=orienter_factory, rng=rng, tag=(root, isoform)))
+            iso[isoform] = pg
+        results[root] = iso
+    batcher.flush()
+    return {root: {isoform: [pg.consensus, pg.names] for isoform, pg in iso.items()} for root, iso in results.items()}
+
+
+def write_isoform_files(roots, results, out_path):
+    """Writer of Isoform_Consensi.fasta and reads2isoforms.txt, byte-compatible with the
+    reference (defineIsoforms.py:155-166): global 1-based counter over loci in `roots` order,
+    then dict order; the name carries the number of ALL reads of the isoform."""
+    counter = 0
+    with open(out_path + "/Isoform_Consensi.fasta", "w") as out, open(out_path + "/reads2isoforms.txt", "w") as out_r2i:
+        for root in roots:
+            iso_data = results[root]
+            for isoform in iso_data:
+                counter += 1
+                consensus, names = iso_data[isoform]
+                name_string = "Isoform" + str(counter) + "_" + str(len(names))
+                out.write(">%s\n%s\n" % (name_string, consensus))
+                for name in names:
+                    out_r2i.write("%s\t%s\n" % (name, name_string))
+    return counter

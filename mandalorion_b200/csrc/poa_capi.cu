@@ -405,6 +405,7 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
     st.band_cells = (int64_t)hs[SI_CELLS]; st.int_ops = (int64_t)hs[SI_INTOPS]; st.full_cells = (int64_t)hs[SI_FULL];
     st.n_alignments = (int64_t)hs[SI_ALN]; st.n_align_i16 = (int64_t)hs[SI_ALN16]; st.n_align_i32 = (int64_t)hs[SI_ALN32];
     st.tb_bytes = (int64_t)hs[SI_TB];
+    for (int k = 0; k < 6; ++k) st.phase_cycles[k] = (int64_t)hs[SI_T_PREP + k];
     st.n_kernel_launches = n_launch;
     ctx->last = st;
     ctx->ran = true;

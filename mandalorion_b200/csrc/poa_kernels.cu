@@ -800,10 +800,15 @@ __device__ int process_group(const KernelArgs &A, const Slot &S, int g, int *rin
         }
         if (len <= 0) continue;
         if ((uint32_t)len > A.L.qcap) return ST_RETRY;
+        long long tk0 = clock64();
         remain_pass(S, par, N, lane);
+        long long tk1 = clock64();
+        st[SI_T_PREP] += tk1 - tk0;
         AlnState R;
         const int rc = dp_align(A, S, par, N, seq, len, ring, ring_info, lane, R);
         if (rc != ST_OK) return rc;
+        tk0 = clock64();
+        st[SI_T_DP] += tk0 - tk1;
         st[SI_CELLS] += R.cells; st[SI_INTOPS] += R.intops; st[SI_FULL] += R.full; st[SI_ALN] += 1;
         st[R.bits == 16 ? SI_ALN16 : SI_ALN32] += 1; st[SI_TB] += R.tbbytes;
         if (lane == 0) {
@@ -817,10 +822,14 @@ __device__ int process_group(const KernelArgs &A, const Slot &S, int g, int *rin
         ok = __shfl_sync(FULL, ok, 0);
         __syncwarp();
         if (!ok) return ST_EMPTY;
+        tk1 = clock64();
+        st[SI_T_TB] += tk1 - tk0;
         const int mrc = merge_read(A, S, par, N, E, seq, len, creator0, tr_aln, tr_node, lane);
         if (mrc != ST_OK) return mrc;
+        st[SI_T_MERGE] += clock64() - tk1;
     }
     if (N <= 2) return ST_EMPTY;
+    const long long tc0 = clock64();
     int clen = 0;
     if (lane == 0) {
         const int cap = (int)(A.cons_off[g + 1] - A.cons_off[g]);
@@ -830,6 +839,7 @@ __device__ int process_group(const KernelArgs &A, const Slot &S, int g, int *rin
     __syncwarp();
     if (clen < 0) return ST_RETRY;
     if (lane == 0) A.cons_len[g] = clen;
+    st[SI_T_CONS] += clock64() - tc0;
     return ST_OK;
 }
 
@@ -853,7 +863,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) poa_group_kernel(const K
         unsigned long long gst[SI_COUNT];
 #pragma unroll
         for (int k = 0; k < SI_COUNT; ++k) gst[k] = 0;
+        const long long tg0 = clock64();
         const int rc = process_group(A, S, g, ring, ring_info, lane, gst);
+        gst[SI_T_BUSY] += clock64() - tg0;
         if (lane == 0) {
             A.status[g] = rc;
             if (rc != ST_OK) A.cons_len[g] = 0;

@@ -32,7 +32,8 @@ class _Stats(C.Structure):
                 ("band_cells", C.c_int64), ("full_cells", C.c_int64), ("int_ops", C.c_int64),
                 ("n_align_i16", C.c_int64), ("n_align_i32", C.c_int64), ("tb_bytes", C.c_int64),
                 ("n_retry_groups", C.c_int64), ("kernel_ms", C.c_double), ("h2d_ms", C.c_double),
-                ("d2h_ms", C.c_double), ("n_kernel_launches", C.c_int64), ("reserved", C.c_int64 * 4)]
+                ("d2h_ms", C.c_double), ("n_kernel_launches", C.c_int64), ("phase_cycles", C.c_int64 * 6),
+                ("reserved", C.c_int64 * 2)]
 
 
 class _Trace(C.Structure):
@@ -157,7 +158,9 @@ class PoaContext:
 
     @staticmethod
     def _stats_dict(st):
-        return {k: getattr(st, k) for k, _ in _Stats._fields_ if k != "reserved"}
+        d = {k: getattr(st, k) for k, _ in _Stats._fields_ if k not in ("reserved", "phase_cycles")}
+        d["phase_cycles"] = dict(zip(("prep", "dp", "traceback", "merge", "consensus", "busy"), list(st.phase_cycles)))
+        return d
 
     # ---- three-stage interface (inputs stay resident in HBM between run() calls) ----
     def upload(self, gro, rbo, bases, flags=None):

@@ -31,7 +31,8 @@ class _Stats(C.Structure):
                 ("band_cells", C.c_int64), ("full_cells", C.c_int64), ("int_ops", C.c_int64),
                 ("n_align_i16", C.c_int64), ("n_align_i32", C.c_int64), ("tb_bytes", C.c_int64),
                 ("n_retry_groups", C.c_int64), ("kernel_ms", C.c_double), ("h2d_ms", C.c_double),
-                ("d2h_ms", C.c_double), ("n_kernel_launches", C.c_int64), ("reserved", C.c_int64 * 4)]
+                ("d2h_ms", C.c_double), ("n_kernel_launches", C.c_int64), ("phase_cycles", C.c_int64 * 6),
+                ("reserved", C.c_int64 * 2)]
 
 
 class _Trace(C.Structure):
@@ -128,5 +129,5 @@ def oracle_consensus_batch(groups=None, packed=None, params=None, n_threads=1, t
         raise RuntimeError(f"mpoa_oracle_consensus_batch failed: {rc}")
     raw = cons_buf.tobytes()
     cons = [raw[cons_off[i]:cons_off[i + 1]] for i in range(ng)]
-    stats = {k: getattr(st, k) for k, _ in _Stats._fields_ if k != "reserved"}
+    stats = {k: getattr(st, k) for k, _ in _Stats._fields_ if k not in ("reserved", "phase_cycles")}
     return dict(cons=cons, status=status, stats=stats, trace=tr_arrays)

@@ -57,7 +57,7 @@ def compare(groups, label, ctx, verbose=True):
     print(f"[{label}] groups={len(groups)} bad={nbad} oracle={t1 - t0:.2f}s gpu_wall={t2 - t1:.2f}s "
           f"kernel={st['kernel_ms']:.1f}ms cells={st['band_cells']} (oracle {o['stats']['band_cells']}) "
           f"GCUPS={st['band_cells'] / max(st['kernel_ms'], 1e-9) / 1e6:.2f} retry={st['n_retry_groups']} "
-          f"launches={st['n_kernel_launches']}")
+          f"launches={st['n_kernel_launches']} phases={ {k: round(v / max(1, st['phase_cycles']['busy']), 3) for k, v in st['phase_cycles'].items()} }")
     return nbad
 
 

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run by the driver with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def built():
+    """The in-tree libraries (oracle always; the CUDA library when it has been built)."""
+    import __graft_entry__ as ge
+    ge.build()
+    return True
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx(built):
+    from mandalorion_b200 import PoaContext
+    ctx = PoaContext(0)          # no fallback: fails loudly without the CUDA library / GPU
+    yield ctx
+    ctx.close()
