@@ -20,11 +20,11 @@
 
 namespace mpoa {
 cudaError_t launch_encode(const uint8_t *ascii, uint8_t *codes, int64_t n, cudaStream_t stream);
-cudaError_t launch_poa(const KernelArgs &A, int n_blocks, int warps_per_block, cudaStream_t stream);
-int poa_max_blocks_per_sm(int wcap, int warps_per_block);
-size_t poa_smem_bytes(int wcap, int warps_per_block);
-cudaError_t launch_gather(const uint8_t *cons, const int64_t *region_off, const int32_t *cons_len,
-                          const int64_t *out_off, uint8_t *out, int64_t n_groups, cudaStream_t stream);
+cudaError_t launch_poa(int variant, const KernelArgs &A, int n_blocks, int warps_per_block, cudaStream_t stream);
+int poa_max_blocks_per_sm(int variant, int wcap, int warps_per_block);
+size_t poa_smem_bytes(int variant, int wcap, int warps_per_block);
+cudaError_t launch_gather(const uint8_t *cons, const int64_t *region_off, const int64_t *out_off, uint8_t *out,
+                          int64_t n_groups, cudaStream_t stream);
 }  // namespace mpoa
 
 using namespace mpoa;
@@ -33,7 +33,10 @@ struct GroupInfo {
     int32_t n_reads, maxlen, minlen;
     int64_t sumlen;
     double cost;
-    int32_t wneed;
+    int32_t wneed;     // expected band width in cells
+    int8_t lanes16;    // 1: every alignment is expected to fit abPOA's int16 lanes
+    int8_t level;      // index into kLevels (kernel variant + band capacity) of the next launch
+    int8_t attempt;    // workspace-capacity escalation
 };
 
 struct mpoa_ctx {
@@ -186,7 +189,15 @@ extern "C" int mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups, const int64_t 
         /* expected band: 2w + length spread + SIMD rounding on both sides + slack */
         const int w = ctx->params.wb + (int)(ctx->params.wf * (float)gi.maxlen);
         gi.wneed = 2 * w + (gi.maxlen - gi.minlen) + 2 * ctx->params.simd_pn_i16 + 48;
+        gi.wneed = std::min(gi.wneed, gi.maxlen + 1 + 2 * ctx->params.simd_pn_i16);
         gi.cost = (double)gi.sumlen * (double)gi.wneed;
+        /* abPOA's own rule for int16 lanes (scores and gap-extended lengths below 32767 minus slack) */
+        const mpoa_params &pp = ctx->params;
+        const int64_t slack = 32767 - std::abs(pp.mismatch) - pp.gap_open1 - pp.gap_ext1 - pp.gap_open2 - pp.gap_ext2;
+        const int64_t est_nodes = (int64_t)(gi.maxlen * (1.0 + 0.02 * gi.n_reads)) + 16 * gi.n_reads + 64;
+        gi.lanes16 = ((int64_t)gi.maxlen * std::abs(pp.match) <= slack &&
+                      std::max<int64_t>(gi.maxlen, est_nodes) * pp.gap_ext1 + pp.gap_open1 <= slack) ? 1 : 0;
+        gi.level = 0; gi.attempt = 0;
     }
     ctx->n_groups = n_groups; ctx->n_reads = n_reads; ctx->n_bases = n_bases;
 
@@ -231,8 +242,8 @@ extern "C" int mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups, const int64_t 
 /* capacities of one launch */
 struct Caps {
     uint32_t ncap, ecap, qcap;
-    uint64_t tbcap, spcap;
-    int wcap;
+    uint64_t tbcap;
+    int wcap, variant;
 };
 
 static uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
@@ -240,7 +251,7 @@ static uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 static SlotLayout make_layout(const Caps &c) {
     SlotLayout L;
     std::memset(&L, 0, sizeof(L));
-    L.ncap = c.ncap; L.ecap = c.ecap; L.qcap = c.qcap; L.tbcap = c.tbcap; L.spcap = c.spcap;
+    L.ncap = c.ncap; L.ecap = c.ecap; L.qcap = c.qcap; L.tbcap = c.tbcap;
     uint64_t off = 0;
     auto take = [&](uint64_t bytes) { uint64_t o = off; off = align_up(off + bytes, 256); return o; };
     const uint64_t n = c.ncap + 2, e = c.ecap + 2, q = c.qcap + 2;
@@ -249,22 +260,32 @@ static SlotLayout make_layout(const Caps &c) {
         L.in_off[p] = take(n * 4); L.in_row[p] = take(e * 4);
         L.out_off[p] = take(n * 4); L.out_row[p] = take(e * 4); L.out_w[p] = take(e * 4);
     }
-    L.remain = take(n * 4); L.meta = take(n * 4); L.rowinfo = take(n * 16); L.tboff = take(n * 4);
-    L.rowbest = take(n * 4); L.spoff = take(n * 4); L.qmap = take(q * 4);
+    L.remain = take(n * 4); L.meta = take(n * 4); L.rowinfo = take(n * 16); L.rowtb = take(n * 8);
+    L.rowbest = take(n * 4); L.qmap = take(q * 4);
     L.pv = take(q * 4); L.pkey = take(q * 4); L.pnew = take(q * 4); L.psib = take(q * 4);
     L.nin = take(q * 4); L.nout = take(q * 4);
     L.cnt = take(n * 4); L.addin = take(n * 4); L.addout = take(n * 4); L.grow = take(n); L.srcof = take(n * 4);
-    L.tb = take(c.tbcap + 16);
-    L.spill = take(c.spcap * 4 + 16);
+    L.tb = take(c.tbcap + 64);
     L.slot_bytes = align_up(off, 1024);
     return L;
 }
 
-static const int kWcapBins[] = {96, 128, 160, 192, 256, 320, 384, 512, 768, 1024, 1536, 2048, 3072, 4096, 6144, 8192};
+/* launch levels: kernel variant (0 = int32 lanes, 2/4/8 = packed int16x2 words per lane) and the
+ * band capacity in cells.  A group escalates along this list when its band or scores outgrow
+ * the level it was scheduled at. */
+struct Level { int variant, wcap; };
+static const Level kLevels[] = {{2, 128}, {4, 256}, {8, 512}, {0, 256}, {0, 512}, {0, 1024}, {0, 2048}, {0, 4096},
+                                {0, 8192}, {0, 16384}};
+static const int kNumLevels = (int)(sizeof(kLevels) / sizeof(kLevels[0]));
 
-static int pick_wcap(int wneed) {
-    for (int b : kWcapBins) if (b >= wneed) return b;
-    return -1;
+static int first_level(bool lanes16, int wneed) {
+    for (int l = 0; l < kNumLevels; ++l)
+        if ((lanes16 || kLevels[l].variant == 0) && kLevels[l].wcap >= wneed) return l;
+    return kNumLevels - 1;
+}
+/* can a group scheduled for level a run in a launch of level b? */
+static bool level_covers(int b, int a, bool lanes16) {
+    return kLevels[b].wcap >= kLevels[a].wcap && (kLevels[b].variant == 0 || lanes16);
 }
 
 /* run one set of groups with one set of capacities; appends groups that need more to `retry` */
@@ -272,9 +293,9 @@ static int run_launch(mpoa_ctx *ctx, const std::vector<int32_t> &groups, const C
     if (groups.empty()) return MPOA_OK;
     /* warps per block: as many (<=4) as the shared-memory ring allows */
     int wpb = 4;
-    while (wpb > 1 && poa_smem_bytes(caps.wcap, wpb) > ctx->smem_optin) wpb >>= 1;
-    if (poa_smem_bytes(caps.wcap, wpb) > ctx->smem_optin) { ctx->err = "band wider than shared memory allows"; return 1; }
-    int bps = poa_max_blocks_per_sm(caps.wcap, wpb);
+    while (wpb > 1 && poa_smem_bytes(caps.variant, caps.wcap, wpb) > ctx->smem_optin) wpb >>= 1;
+    if (poa_smem_bytes(caps.variant, caps.wcap, wpb) > ctx->smem_optin) { ctx->err = "band wider than shared memory allows"; return 1; }
+    int bps = poa_max_blocks_per_sm(caps.variant, caps.wcap, wpb);
     if (bps <= 0) { ctx->err = "kernel cannot be resident (shared memory)"; return MPOA_ECUDA; }
     const SlotLayout L = make_layout(caps);
     size_t free_b = 0, total_b = 0;
@@ -310,7 +331,7 @@ static int run_launch(mpoa_ctx *ctx, const std::vector<int32_t> &groups, const C
     A.P.oe1 = p.gap_open1 + p.gap_ext1; A.P.oe2 = p.gap_open2 + p.gap_ext2;
     A.P.wb = p.wb; A.P.wf = p.wf; A.P.pn16 = p.simd_pn_i16; A.P.pn32 = p.simd_pn_i32;
     A.wcap = caps.wcap;
-    CK(launch_poa(A, (int)n_blocks, wpb, ctx->stream));
+    CK(launch_poa(caps.variant, A, (int)n_blocks, wpb, ctx->stream));
     ++*n_launch;
     return MPOA_OK;
 }
@@ -331,67 +352,94 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
 
     std::vector<int32_t> pending(ng);
     std::iota(pending.begin(), pending.end(), 0);
+    for (int64_t g = 0; g < ng; ++g) {
+        GroupInfo &gi = ctx->ginfo[g];
+        gi.level = (int8_t)first_level(gi.lanes16 != 0, gi.wneed);
+        gi.attempt = 0;
+    }
     int64_t n_launch = 0;
-    const int kMaxAttempt = 4;
-    for (int attempt = 0; attempt < kMaxAttempt && !pending.empty(); ++attempt) {
-        /* bin by ring width; inside a bin the heaviest groups go first */
-        std::vector<std::pair<int, std::vector<int32_t>>> bins;
-        for (int32_t g : pending) {
-            const GroupInfo &gi = ctx->ginfo[g];
-            int wneed = gi.wneed;
-            for (int a = 0; a < attempt; ++a) wneed = wneed * 3 + 64;
-            int wc = pick_wcap(std::min(wneed, gi.maxlen + 1 + 2 * ctx->params.simd_pn_i16));
-            if (wc < 0) wc = kWcapBins[sizeof(kWcapBins) / sizeof(int) - 1];
-            auto it = std::find_if(bins.begin(), bins.end(), [&](const auto &b) { return b.first == wc; });
-            if (it == bins.end()) { bins.push_back({wc, {}}); it = bins.end() - 1; }
-            it->second.push_back(g);
+    std::vector<int32_t> dstat(ng);
+    for (int round = 0; round < 12 && !pending.empty(); ++round) {
+        /* one launch per level; a level with too few groups to fill the GPU is folded into a
+         * wider level that covers it (launches of one batch are serialised) */
+        std::vector<std::vector<int32_t>> bins(kNumLevels);
+        for (int32_t g : pending) bins[ctx->ginfo[g].level].push_back(g);
+        const size_t min_groups = (size_t)ctx->n_sm * 8;
+        for (int a = 0; a < kNumLevels; ++a) {
+            if (bins[a].empty() || bins[a].size() >= min_groups) continue;
+            bool all16 = true;
+            for (int32_t g : bins[a]) all16 = all16 && ctx->ginfo[g].lanes16;
+            for (int b = 0; b < kNumLevels; ++b) {
+                if (b == a || bins[b].empty() || !level_covers(b, a, all16)) continue;
+                bins[b].insert(bins[b].end(), bins[a].begin(), bins[a].end());
+                bins[a].clear();
+                break;
+            }
         }
-        std::sort(bins.begin(), bins.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
-        for (auto &bin : bins) {
-            auto &gs = bin.second;
+        for (int lv = 0; lv < kNumLevels; ++lv) {
+            auto &gs = bins[lv];
+            if (gs.empty()) continue;
             std::sort(gs.begin(), gs.end(), [&](int32_t a, int32_t b) {
                 const double ca = ctx->ginfo[a].cost, cb = ctx->ginfo[b].cost;
                 return ca != cb ? ca > cb : a < b;
             });
             Caps c;
-            c.wcap = bin.first;
-            uint64_t ncap = 0, qcap = 0, sum_max = 0;
+            c.wcap = kLevels[lv].wcap; c.variant = kLevels[lv].variant;
+            uint64_t ncap = 0, qcap = 0, sum_max = 0, tbmax = 0;
+            int att_max = 0;
+            const uint64_t cell_bytes = c.variant == 0 ? 12 : 6;
             for (int32_t g : gs) {
                 const GroupInfo &gi = ctx->ginfo[g];
                 uint64_t est;
-                if (attempt == 0) est = (uint64_t)(gi.maxlen * (1.0 + 0.03 * gi.n_reads)) + 32ull * gi.n_reads + 256;
-                else if (attempt == 1) est = (uint64_t)(gi.maxlen * (1.0 + 0.15 * gi.n_reads)) + 64ull * gi.n_reads + 1024;
+                if (gi.attempt == 0) est = (uint64_t)(gi.maxlen * (1.0 + 0.02 * gi.n_reads)) + 24ull * gi.n_reads + 256;
+                else if (gi.attempt == 1) est = (uint64_t)(gi.maxlen * (1.0 + 0.15 * gi.n_reads)) + 64ull * gi.n_reads + 1024;
                 else est = (uint64_t)gi.sumlen + 2;
                 est = std::min<uint64_t>(est, (uint64_t)gi.sumlen + 2);
                 ncap = std::max(ncap, est);
                 qcap = std::max<uint64_t>(qcap, gi.maxlen);
                 sum_max = std::max<uint64_t>(sum_max, gi.sumlen);
+                att_max = std::max<int>(att_max, gi.attempt);
+                const uint64_t wrow = std::min<uint64_t>(std::min<uint64_t>(c.wcap, gi.maxlen + 64),
+                                                         gi.attempt == 0 ? (uint64_t)gi.wneed : (uint64_t)c.wcap) + 16;
+                tbmax = std::max<uint64_t>(tbmax, est * wrow * cell_bytes);
             }
             c.ncap = (uint32_t)std::min<uint64_t>(ncap + 8, 0x7fffff00u);
-            c.ecap = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(2ull * c.ncap + 64, sum_max + 4096), 0x7fffff00u);
-            if (attempt >= 2) c.ecap = (uint32_t)std::min<uint64_t>(sum_max + 4096, 0x7fffff00u);
+            c.ecap = (uint32_t)std::min<uint64_t>(att_max >= 2 ? sum_max + 4096 : std::min<uint64_t>(2ull * c.ncap + 64, sum_max + 4096),
+                                                  0x7fffff00u);
             c.qcap = (uint32_t)qcap + 8;
-            const uint64_t wfull = std::min<uint64_t>((uint64_t)c.wcap, qcap + 1 + 64);
-            c.tbcap = std::min<uint64_t>((uint64_t)c.ncap * wfull * (attempt == 0 ? 2 : 4), 0xfff00000ull);
-            c.spcap = std::min<uint64_t>((uint64_t)c.ncap * wfull * 3 / (attempt == 0 ? 8 : (attempt == 1 ? 2 : 1)) + 4096, 0x3ff00000ull);
+            c.tbcap = std::min<uint64_t>(tbmax + 4096, 0x3fff00000ull);
             int rc = run_launch(ctx, gs, c, &n_launch);
             if (rc < 0) return rc;
             if (rc > 0) {  // cannot be run with these capacities at all: treated like an abpoa failure
                 for (int32_t g : gs) ctx->h_status[g] = ST_EMPTY;
-                gs.clear();
             }
         }
         CK(cudaStreamSynchronize(ctx->stream));
-        /* collect statuses of what was launched */
-        std::vector<int32_t> dstat(ng);
         CK(cudaMemcpy(dstat.data(), ctx->d_status, ng * sizeof(int32_t), cudaMemcpyDeviceToHost));
         std::vector<int32_t> next;
         for (int32_t g : pending) {
             if (ctx->h_status[g] == ST_EMPTY) continue;  // not launchable
-            if (dstat[g] == ST_RETRY) next.push_back(g);
-            else ctx->h_status[g] = dstat[g];
+            GroupInfo &gi = ctx->ginfo[g];
+            if (dstat[g] == ST_RETRY) {
+                if (gi.attempt >= 3) { ctx->h_status[g] = ST_EMPTY; continue; }
+                gi.attempt++;
+                next.push_back(g);
+            } else if (dstat[g] == ST_RETRY_WIDE || dstat[g] == ST_RETRY_32) {
+                int lv = gi.level, nl = -1;
+                if (dstat[g] == ST_RETRY_32) {
+                    gi.lanes16 = 0;
+                    for (int b = 0; b < kNumLevels; ++b)
+                        if (kLevels[b].variant == 0 && kLevels[b].wcap >= kLevels[lv].wcap) { nl = b; break; }
+                } else {
+                    for (int b = 0; b < kNumLevels; ++b)
+                        if (kLevels[b].wcap > kLevels[lv].wcap && (kLevels[b].variant == 0 || gi.lanes16)) { nl = b; break; }
+                }
+                if (nl < 0) { ctx->h_status[g] = ST_EMPTY; continue; }
+                gi.level = (int8_t)nl;
+                next.push_back(g);
+            } else ctx->h_status[g] = dstat[g];
         }
-        if (attempt == 0) st.n_retry_groups = (int64_t)next.size();
+        if (round == 0) st.n_retry_groups = (int64_t)next.size();
         pending.swap(next);
     }
     for (int32_t g : pending) ctx->h_status[g] = ST_EMPTY;  // still too big after the last attempt
@@ -439,7 +487,7 @@ extern "C" int mpoa_batch_fetch(mpoa_ctx *ctx, int64_t *cons_off, uint8_t *cons_
         CK(cudaMalloc(&d_out_off, (ng + 1) * sizeof(int64_t)));
         CK(cudaMalloc(&d_out, total));
         CK(cudaMemcpyAsync(d_out_off, cons_off, (ng + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-        CK(launch_gather(ctx->d_cons, ctx->d_region_off, ctx->d_cons_len, d_out_off, d_out, ng, ctx->stream));
+        CK(launch_gather(ctx->d_cons, ctx->d_region_off, d_out_off, d_out, ng, ctx->stream));
         CK(cudaMemcpyAsync(cons_buf, d_out, total, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         cudaFree(d_out_off);

@@ -13,9 +13,11 @@
  *     After every read the graph is re-emitted (double buffered) with the new nodes merged in,
  *     so there is never a BFS re-sort; abPOA's results do not depend on which valid
  *     topological order is used (every tie-break iterates edge lists, never row numbers);
- *   - DP rows H/E1/E2 live in a per-warp shared-memory ring; rows with a far successor are
- *     additionally spilled to HBM;
- *   - traceback is flag based: 1 byte per band cell (4 for rows with several predecessors).
+ *   - DP rows H/E1/E2 live in a per-warp shared-memory ring (int16x2 packed, DPX
+ *     VIADDMNMX/VIMNMX3, for alignments abPOA itself would run in int16 lanes; int32 otherwise);
+ *     every row is also streamed to HBM (the traceback matrices) with vectorised stores;
+ *   - traceback compares the stored values exactly like abPOA's cg_backtrack and recomputes the
+ *     insertion scores F of a row only when a step needs them.
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -24,11 +26,13 @@
 namespace mpoa {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int NEG = -(1 << 28);  // -inf surrogate of the int32 path
-constexpr int RING = 8;          // rows kept in the shared-memory ring
+constexpr int NEG = -(1 << 28);      // -inf surrogate in int32 arithmetic
+constexpr int NEG16 = -30000;        // -inf surrogate / floor of the packed int16 path
+constexpr int RING = 8;              // rows kept in the shared-memory ring
 constexpr int WARPS_PER_BLOCK = 4;
+constexpr int RING_PAD = 4;          // words of padding on each side of a packed ring row
 
-enum GroupStatus : int { ST_OK = 0, ST_EMPTY = 1, ST_RETRY = 2, ST_PENDING = 3 };
+enum GroupStatus : int { ST_OK = 0, ST_EMPTY = 1, ST_RETRY = 2, ST_PENDING = 3, ST_RETRY_WIDE = 4, ST_RETRY_32 = 5 };
 
 struct DevParams {
     int match, mismatch, o1, e1, o2, e2, oe1, oe2, wb;
@@ -39,12 +43,12 @@ struct DevParams {
 /* byte offsets of the arrays inside one warp's HBM workspace ("slot") */
 struct SlotLayout {
     uint32_t ncap, ecap, qcap;
-    uint64_t tbcap, spcap;
+    uint64_t tbcap;                                    // bytes of the traceback area
     uint64_t base[2], sib[2], creator[2], in_off[2], in_row[2], out_off[2], out_row[2], out_w[2];
-    uint64_t remain, meta, rowinfo, tboff, rowbest, spoff, qmap;
+    uint64_t remain, meta, rowinfo, rowtb, rowbest, qmap;
     uint64_t pv, pkey, pnew, psib, nin, nout;          // per query position
     uint64_t cnt, addin, addout, grow, srcof;          // per row
-    uint64_t tb, spill;
+    uint64_t tb;
     uint64_t slot_bytes;
 };
 
@@ -71,5 +75,9 @@ struct KernelArgs {
 
 enum StatIdx { SI_CELLS = 0, SI_INTOPS, SI_FULL, SI_ALN, SI_ALN16, SI_ALN32, SI_TB,
                SI_T_PREP, SI_T_DP, SI_T_TB, SI_T_MERGE, SI_T_CONS, SI_T_BUSY, SI_COUNT };
+
+/* kernel variants: 0 = int32 lanes, any band width (chunks of 32 cells);
+ * 2/4/8 = packed int16x2, that many 32-bit words (pairs of cells) per lane: band <= 128/256/512 */
+constexpr int kVariants[] = {0, 2, 4, 8};
 
 }  // namespace mpoa

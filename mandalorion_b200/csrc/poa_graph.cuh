@@ -1,0 +1,367 @@
+/*
+ * poa_graph.cuh -- the POA graph in row space: workspace accessors, warp scans, first read,
+ * remain pass, merge of an aligned read, heaviest-bundle consensus.
+ * Semantics follow abPOA v1.4.1 as invoked by the reference (utils/SpliceDefineConsensus.py:917):
+ * add_graph_sequence / add_subgraph_alignment / BFS_set_node_remain / heaviest_bundling.
+ */
+#pragma once
+#include <climits>
+#include "poa_device.cuh"
+
+namespace mpoa {
+
+/* One warp's HBM workspace.  Only the base pointer is held in registers: every array address is
+ * base + an offset read from the kernel parameter block (constant bank), so the ~35 array
+ * pointers never occupy registers or spill to local memory.  The graph is double buffered:
+ * x_p() is the CURRENT graph, n_x_p() the buffer the next merge writes. */
+struct Slot {
+    uint8_t *b;
+    int par;
+};
+
+#define MPOA_ACC(T, name)                                                                       \
+    __device__ __forceinline__ T *name##_p(const KernelArgs &A, const Slot &S) {                \
+        return reinterpret_cast<T *>(S.b + A.L.name);                                           \
+    }
+#define MPOA_ACC2(T, name)                                                                      \
+    __device__ __forceinline__ T *name##_p(const KernelArgs &A, const Slot &S) {                \
+        return reinterpret_cast<T *>(S.b + A.L.name[S.par]);                                    \
+    }                                                                                           \
+    __device__ __forceinline__ T *n_##name##_p(const KernelArgs &A, const Slot &S) {            \
+        return reinterpret_cast<T *>(S.b + A.L.name[S.par ^ 1]);                                \
+    }
+MPOA_ACC2(uint8_t, base) MPOA_ACC2(uint8_t, sib) MPOA_ACC2(int32_t, creator)
+MPOA_ACC2(uint32_t, in_off) MPOA_ACC2(uint32_t, in_row) MPOA_ACC2(uint32_t, out_off)
+MPOA_ACC2(uint32_t, out_row) MPOA_ACC2(int32_t, out_w)
+MPOA_ACC(int32_t, remain) MPOA_ACC(uint32_t, meta) MPOA_ACC(int4, rowinfo) MPOA_ACC(uint2, rowtb)
+MPOA_ACC(int32_t, rowbest) MPOA_ACC(int32_t, qmap)
+MPOA_ACC(int32_t, pv) MPOA_ACC(int32_t, pkey) MPOA_ACC(int32_t, pnew) MPOA_ACC(int32_t, psib)
+MPOA_ACC(int32_t, nin) MPOA_ACC(int32_t, nout)
+MPOA_ACC(int32_t, cnt) MPOA_ACC(int32_t, addin) MPOA_ACC(int32_t, addout) MPOA_ACC(int32_t, srcof)
+MPOA_ACC(uint8_t, grow) MPOA_ACC(uint8_t, tb)
+
+__device__ __forceinline__ Slot make_slot(const KernelArgs &A, int slot, int par) {
+    Slot S;
+    S.b = A.ws + (uint64_t)slot * A.L.slot_bytes;
+    S.par = par;
+    return S;
+}
+
+__device__ __forceinline__ int warp_incl_sum(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(FULL, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ int warp_incl_max(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(FULL, v, d);
+        if (lane >= d) v = max(v, t);
+    }
+    return v;
+}
+
+/* inclusive scan of  S[l] = max_{k<=l} (x[k] - e*(l-k))  -- the insertion (F) recurrence */
+__device__ __forceinline__ int warp_scan_decay(int v, int e, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(FULL, v, d);
+        if (lane >= d) v = max(v, t - d * e);
+    }
+    return v;
+}
+
+enum MetaBits { META_BASE = 7, META_FAR = 8, META_TOSINK = 16 };
+
+/* ------------------------------------------------------------------------------------------ */
+/* graph: first read, remain pass                                                              */
+/* ------------------------------------------------------------------------------------------ */
+
+/* first read = linear chain src -> b0 -> ... -> sink, every edge weight 1 */
+__device__ __forceinline__ void init_graph(const KernelArgs &A, const Slot &S, const uint8_t *seq, int len, int creator0, int lane) {
+    const int N = len + 2;
+    for (int r = lane; r <= N; r += 32) {
+        if (r < N) {
+            const bool real = r >= 1 && r <= len;
+            base_p(A, S)[r] = real ? seq[r - 1] : 0;
+            sib_p(A, S)[r] = 0;
+            creator_p(A, S)[r] = real ? creator0 + r - 1 : -1;
+            if (r >= 1) in_row_p(A, S)[r - 1] = r - 1;
+            if (r < N - 1) { out_row_p(A, S)[r] = r + 1; out_w_p(A, S)[r] = 1; }
+        }
+        in_off_p(A, S)[r] = r == 0 ? 0 : r - 1;
+        out_off_p(A, S)[r] = r < N - 1 ? r : N - 1;
+    }
+    __syncwarp();
+}
+
+/*
+ * remain[r] = remain[heaviest out-neighbour (first maximum)] + 1, remain[sink] = -1: what abPOA's
+ * reverse BFS computes.  Rows are handled 32 at a time from the sink side; in-window chains are
+ * resolved by pointer jumping.  Also emits the per-row meta word used by the DP.
+ */
+__device__ __forceinline__ void remain_pass(const KernelArgs &A, const Slot &S, int N, int lane) {
+    const uint32_t *out_off = out_off_p(A, S), *out_row = out_row_p(A, S);
+    const int32_t *out_w = out_w_p(A, S);
+    if (lane == 0) {
+        remain_p(A, S)[N - 1] = -1;
+        meta_p(A, S)[N - 1] = 0;
+    }
+    int prev_vals = 0;  // remain of rows [w0+32, w0+64)
+    for (int w0 = ((N - 2) / 32) * 32; w0 >= 0; w0 -= 32) {
+        const int r = w0 + lane;
+        const bool active = r <= N - 2;
+        int hs = N - 1, maxrow = 0, tosink = 0;
+        if (active) {
+            const uint32_t o0 = out_off[r], o1 = out_off[r + 1];
+            int maxw = -1;
+            for (uint32_t e = o0; e < o1; ++e) {
+                const int t = (int)out_row[e], w = out_w[e];
+                if (w > maxw) { maxw = w; hs = t; }
+                maxrow = max(maxrow, t);
+                tosink |= (t == N - 1);
+            }
+        }
+        int acc, nxt = -1;
+        const int src_prev = min(31, max(0, hs - (w0 + 32)));
+        const int from_prev = __shfl_sync(FULL, prev_vals, src_prev);
+        if (!active) acc = 0;
+        else if (hs == N - 1) acc = 0;
+        else if (hs >= w0 + 64) acc = remain_p(A, S)[hs] + 1;
+        else if (hs >= w0 + 32) acc = from_prev + 1;
+        else { acc = 1; nxt = hs - w0; }
+#pragma unroll
+        for (int it = 0; it < 5; ++it) {
+            const int sl = max(nxt, 0);
+            const int a = __shfl_sync(FULL, acc, sl);
+            const int n = __shfl_sync(FULL, nxt, sl);
+            if (nxt >= 0) { acc += a; nxt = n; }
+        }
+        if (active) {
+            remain_p(A, S)[r] = acc;
+            meta_p(A, S)[r] = (uint32_t)base_p(A, S)[r] | ((maxrow - r >= RING) ? META_FAR : 0) | (tosink ? META_TOSINK : 0);
+        }
+        prev_vals = acc;
+        __syncwarp();
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* graph merge                                                                                 */
+/* ------------------------------------------------------------------------------------------ */
+
+/*
+ * Adds the aligned read to the graph (semantics of abPOA's add_subgraph_alignment) and re-emits
+ * the graph into the other buffer with the new nodes merged into the row order:
+ *   - a base aligned to a node with the same base, or to an aligned sibling with the same base,
+ *     reuses that node; otherwise it becomes a new node (a new sibling if it was aligned);
+ *   - new nodes are placed after the end of the sibling group of the previous path node
+ *     (new siblings: after the end of the group they join), in path order;
+ *   - path edges that exist get weight +1, the others are appended to the END of the edge lists
+ *     of their endpoints (edge order = first-creation order).
+ * Returns ST_OK or ST_RETRY (capacity).
+ */
+__device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, int &par, int &N, int &E, const uint8_t *__restrict__ q,
+                          int qlen, int creator0, int32_t *tr_aln, int32_t *tr_node, int lane) {
+    const uint8_t *base = base_p(A, S), *sib = sib_p(A, S);
+    const uint32_t *out_off = out_off_p(A, S), *out_row = out_row_p(A, S), *in_off = in_off_p(A, S), *in_row = in_row_p(A, S);
+    int32_t *out_w = out_w_p(A, S);
+
+    for (int r = lane; r < N; r += 32) { cnt_p(A, S)[r] = 0; addin_p(A, S)[r] = -1; addout_p(A, S)[r] = -1; grow_p(A, S)[r] = 0; }
+    __syncwarp();
+
+    /* U1: resolve every query base to an existing row or a new node; order keys */
+    int carry_key = 0, carry_new = 0;
+    for (int t0 = 0; t0 < qlen; t0 += 32) {
+        const int t = t0 + lane;
+        int isnew = 0, v = -1, key = -1, sibof = -1;
+        if (t < qlen) {
+            const int r = qmap_p(A, S)[t];
+            const int b = q[t];
+            if (r >= 0) {
+                if (base[r] == b) v = r;
+                else {
+                    const int sb = sib[r], before = sb >> 4, after = sb & 15;
+                    for (int x = r - before; x <= r + after; ++x)
+                        if (x != r && base[x] == b) v = x;
+                    if (v < 0) { isnew = 1; sibof = r; key = r + after; }
+                }
+                if (!isnew) key = v + (sib[v] & 15);
+                if (tr_aln) tr_aln[t] = creator_p(A, S)[r];
+            } else {
+                isnew = 1;
+                if (tr_aln) tr_aln[t] = -1;
+            }
+            if (tr_node) tr_node[t] = isnew ? creator0 + t : creator_p(A, S)[v];
+        }
+        int ks = warp_incl_max(key, lane);
+        ks = max(ks, carry_key);
+        const int incl = warp_incl_sum(isnew, lane);
+        const int nidx = carry_new + incl - isnew;
+        if (t < qlen) {
+            pv_p(A, S)[t] = isnew ? -1 : v;
+            pkey_p(A, S)[t] = ks;
+            pnew_p(A, S)[t] = nidx;
+            psib_p(A, S)[t] = sibof;
+            if (isnew) atomicAdd(&cnt_p(A, S)[ks], 1);
+            if (sibof >= 0) {
+                const int sb = sib[sibof];
+                for (int x = sibof - (sb >> 4); x <= sibof + (sb & 15); ++x) grow_p(A, S)[x] = 1;
+            }
+        }
+        carry_key = __shfl_sync(FULL, ks, 31);
+        carry_new += __shfl_sync(FULL, incl, 31);
+    }
+    const int n_new = carry_new;
+    const int N2 = N + n_new;
+    if ((uint32_t)N2 > A.L.ncap) return ST_RETRY;
+    __syncwarp();
+
+    /* U2: shift[r] = number of new nodes placed before old row r (exclusive scan of cnt) */
+    {
+        int carry = 0;
+        for (int r0 = 0; r0 < N; r0 += 32) {
+            const int r = r0 + lane;
+            const int c = r < N ? cnt_p(A, S)[r] : 0;
+            const int incl = warp_incl_sum(c, lane);
+            if (r < N) {
+                const int sh = carry + incl - c;
+                cnt_p(A, S)[r] = sh;
+                srcof_p(A, S)[r + sh] = r;
+            }
+            carry += __shfl_sync(FULL, incl, 31);
+        }
+        for (int t = lane; t < qlen; t += 32)
+            if (pv_p(A, S)[t] < 0) srcof_p(A, S)[pkey_p(A, S)[t] + 1 + pnew_p(A, S)[t]] = -(t + 1);
+    }
+    __syncwarp();
+
+    /* U3: the path edges u[t-1] -> u[t], t = 0..qlen (u[-1] = source, u[qlen] = sink) */
+    int n_new_edges = 0;
+    for (int t = lane; t <= qlen; t += 32) {
+        const int from_old = t == 0 ? 0 : pv_p(A, S)[t - 1];
+        const int to_old = t == qlen ? N - 1 : pv_p(A, S)[t];
+        const int from_new = from_old >= 0 ? from_old + cnt_p(A, S)[from_old] : pkey_p(A, S)[t - 1] + 1 + pnew_p(A, S)[t - 1];
+        const int to_new = to_old >= 0 ? to_old + cnt_p(A, S)[to_old] : pkey_p(A, S)[t] + 1 + pnew_p(A, S)[t];
+        bool found = false;
+        if (from_old >= 0 && to_old >= 0) {
+            const uint32_t o0 = out_off[from_old], o1 = out_off[from_old + 1];
+            for (uint32_t e = o0; e < o1; ++e)
+                if ((int)out_row[e] == to_old) { out_w[e] += 1; found = true; break; }
+        }
+        if (!found) {
+            ++n_new_edges;
+            if (from_old >= 0) addout_p(A, S)[from_old] = to_new; else nout_p(A, S)[t - 1] = to_new;
+            if (to_old >= 0) addin_p(A, S)[to_old] = from_new; else nin_p(A, S)[t] = from_new;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n_new_edges += __shfl_xor_sync(FULL, n_new_edges, d);
+    const int E2 = E + n_new_edges;
+    if ((uint32_t)E2 > A.L.ecap) return ST_RETRY;
+    __syncwarp();
+
+    /* U4: emit the merged graph */
+    {
+        int carry_in = 0, carry_out = 0;
+        for (int r0 = 0; r0 < N2; r0 += 32) {
+            const int nr = r0 + lane;
+            int din = 0, dout = 0, src = 0;
+            if (nr < N2) {
+                src = srcof_p(A, S)[nr];
+                if (src >= 0) {
+                    din = (int)(in_off[src + 1] - in_off[src]) + (addin_p(A, S)[src] >= 0);
+                    dout = (int)(out_off[src + 1] - out_off[src]) + (addout_p(A, S)[src] >= 0);
+                } else din = dout = 1;
+            }
+            const int iin = warp_incl_sum(din, lane), iout = warp_incl_sum(dout, lane);
+            if (nr < N2) {
+                uint32_t io = carry_in + iin - din, oo = carry_out + iout - dout;
+                n_in_off_p(A, S)[nr] = io;
+                n_out_off_p(A, S)[nr] = oo;
+                if (src >= 0) {
+                    for (uint32_t e = in_off[src]; e < in_off[src + 1]; ++e) {
+                        const int x = (int)in_row[e];
+                        n_in_row_p(A, S)[io++] = x + cnt_p(A, S)[x];
+                    }
+                    if (addin_p(A, S)[src] >= 0) n_in_row_p(A, S)[io++] = addin_p(A, S)[src];
+                    for (uint32_t e = out_off[src]; e < out_off[src + 1]; ++e) {
+                        const int y = (int)out_row[e];
+                        n_out_row_p(A, S)[oo] = y + cnt_p(A, S)[y];
+                        n_out_w_p(A, S)[oo++] = out_w[e];
+                    }
+                    if (addout_p(A, S)[src] >= 0) { n_out_row_p(A, S)[oo] = addout_p(A, S)[src]; n_out_w_p(A, S)[oo++] = 1; }
+                    n_base_p(A, S)[nr] = base[src];
+                    n_sib_p(A, S)[nr] = (uint8_t)(sib[src] + grow_p(A, S)[src]);
+                    n_creator_p(A, S)[nr] = creator_p(A, S)[src];
+                } else {
+                    const int t = -src - 1;
+                    n_in_row_p(A, S)[io] = nin_p(A, S)[t];
+                    n_out_row_p(A, S)[oo] = nout_p(A, S)[t];
+                    n_out_w_p(A, S)[oo] = 1;
+                    n_base_p(A, S)[nr] = q[t];
+                    const int so = psib_p(A, S)[t];
+                    int sb = 0;
+                    if (so >= 0) { const int o = sib[so]; sb = ((o >> 4) + (o & 15) + 1) << 4; }
+                    n_sib_p(A, S)[nr] = (uint8_t)sb;
+                    n_creator_p(A, S)[nr] = creator0 + t;
+                }
+            }
+            carry_in += __shfl_sync(FULL, iin, 31);
+            carry_out += __shfl_sync(FULL, iout, 31);
+        }
+        if (lane == 0) { n_in_off_p(A, S)[N2] = carry_in; n_out_off_p(A, S)[N2] = carry_out; }
+    }
+    __syncwarp();
+    par ^= 1; N = N2; E = E2;
+    return ST_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* consensus                                                                                   */
+/* ------------------------------------------------------------------------------------------ */
+
+/* heaviest bundling (semantics of abPOA's abpoa_heaviest_bundling, one consensus): reverse sweep
+ * over the row order, then the path source -> sink.  Lane 0.  Returns length or -1 (capacity). */
+__device__ __forceinline__ int heaviest_bundle(const KernelArgs &A, const Slot &S, int N, uint8_t *cons, int cap) {
+    const uint32_t *out_off = out_off_p(A, S), *out_row = out_row_p(A, S);
+    const int32_t *out_w = out_w_p(A, S);
+    int32_t *score = cnt_p(A, S), *maxout = addin_p(A, S);
+    score[N - 1] = 0;
+    maxout[N - 1] = -1;
+    for (int r = N - 2; r >= 0; --r) {
+        const uint32_t o0 = out_off[r], o1 = out_off[r + 1];
+        int max_id = -1;
+        if (r == 0) {
+            int path_score = -1, path_max_w = -1;
+            for (uint32_t e = o0; e < o1; ++e) {
+                const int t = (int)out_row[e], w = out_w[e];
+                if (w > path_max_w || (w == path_max_w && score[t] > path_score)) {
+                    max_id = t; path_score = score[t]; path_max_w = w;
+                }
+            }
+        } else {
+            int max_w = INT_MIN;
+            for (uint32_t e = o0; e < o1; ++e) {
+                const int t = (int)out_row[e], w = out_w[e];
+                if (max_w < w) { max_w = w; max_id = t; }
+                else if (max_w == w && score[max_id] <= score[t]) max_id = t;
+            }
+            score[r] = max_w + score[max_id];
+        }
+        maxout[r] = max_id;
+    }
+    int len = 0, curr = maxout[0];
+    while (curr != N - 1 && curr >= 0) {
+        if (len >= cap) return -1;
+        cons[len++] = "ACGTN"[base_p(A, S)[curr]];
+        curr = maxout[curr];
+    }
+    return len;
+}
+
+}  // namespace mpoa

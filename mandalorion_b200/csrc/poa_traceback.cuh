@@ -1,0 +1,176 @@
+/*
+ * poa_traceback.cuh -- traceback over the stored band rows, by VALUE comparison, in the order and
+ * with the open/extend state machine of abPOA's cg_backtrack (the
+ * reference obtains it from `abpoa -M 5 -r 0`, utils/SpliceDefineConsensus.py:917):
+ *   at (i,j):  1. diagonal  : first predecessor p (edge order) with j-1 inside p's band and
+ *                             H[p][j-1] + s == H[i][j]
+ *              2. deletion  : first p with j inside p's band and H[i][j] == Eout1[p][j] (then
+ *                             Eout2), open vs extend decided by H[p][j] - oe == Eout[p][j]
+ *              3. insertion : H[i][j] == F1[i][j] (then F2), open vs extend likewise
+ * F is not stored: it is recomputed for the one row that needs it (rare: only when a step is
+ * neither a diagonal nor a deletion) by all lanes of the warp.
+ * The whole warp executes the traceback uniformly; lane 0 writes qmap.
+ */
+#pragma once
+#include "poa_dp.cuh"
+
+namespace mpoa {
+
+enum TbOps { OP_M = 1, OP_E1 = 2, OP_E2 = 4, OP_E = 6, OP_F1 = 8, OP_F2 = 16, OP_F = 24, OP_ALL = 31 };
+
+template <typename T>
+struct RowView {
+    const T *h;       // H at h[j - beg], Eout1 at h[stride + ...], Eout2 at h[2*stride + ...]
+    int beg, end, hi, stride, beg_sn, end_sn;
+};
+
+template <typename T>
+__device__ __forceinline__ RowView<T> row_view(const KernelArgs &A, const Slot &S, int r, int lg, int qlen) {
+    RowView<T> v;
+    const int4 info = rowinfo_p(A, S)[r];
+    const uint2 rt = rowtb_p(A, S)[r];
+    v.beg_sn = info.x; v.end_sn = info.y;
+    v.beg = info.x << lg;
+    v.end = ((info.y + 1) << lg) - 1;
+    v.hi = min(v.end, qlen);
+    v.stride = (int)rt.y;
+    v.h = reinterpret_cast<const T *>(reinterpret_cast<const uint32_t *>(tb_p(A, S)) + rt.x);
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ int rv_get(const RowView<T> &v, int arr, int j) {
+    return (j >= v.beg && j <= v.hi) ? (int)v.h[arr * v.stride + (j - v.beg)] : NEG;
+}
+
+__device__ __forceinline__ int score_of(const DevParams &P, int nbase, int qb) {
+    return (nbase >= 4 || qb >= 4) ? 0 : (nbase == qb ? P.match : -P.mismatch);
+}
+
+/* Hhat[i][k] = max(M + s, Ein1, Ein2): the pre-insertion score the DP used for cell (i,k) */
+template <typename T>
+__device__ __forceinline__ int hhat_cell(const KernelArgs &A, const Slot &S, const RowView<T> &vi, int i, int k, int nbase,
+                                         const uint8_t *__restrict__ q, int qlen, int lg) {
+    const uint32_t *in_off = in_off_p(A, S), *in_row = in_row_p(A, S);
+    const int in0 = (int)in_off[i], npre = (int)in_off[i + 1] - in0;
+    int mx = NEG, e1 = NEG, e2 = NEG;
+    for (int kk = 0; kk < npre; ++kk) {
+        const int p = (int)in_row[in0 + kk];
+        const RowView<T> vp = row_view<T>(A, S, p, lg, qlen);
+        const int lo = max(vi.beg_sn, vp.beg_sn) << lg;
+        const int hi = min(((min(vi.end_sn, vp.end_sn) + 1) << lg) - 1, qlen);
+        if (k >= lo && k <= hi) {
+            if (k > lo) mx = max(mx, (int)vp.h[k - 1 - vp.beg]);
+            e1 = max(e1, (int)vp.h[vp.stride + k - vp.beg]);
+            e2 = max(e2, (int)vp.h[2 * vp.stride + k - vp.beg]);
+        }
+    }
+    const int s = k > 0 ? score_of(A.P, nbase, q[k - 1]) : 0;
+    return max(mx + s, max(e1, e2));
+}
+
+/* F1/F2 of row i at columns j and j-1 (what the DP had before taking H = max(Hhat, F1, F2)) */
+template <typename T>
+__device__ __forceinline__ void f_values(const KernelArgs &A, const Slot &S, const RowView<T> &vi, int i, int j, int nbase,
+                                         const uint8_t *__restrict__ q, int qlen, int lg, int lane, int f[4]) {
+    const DevParams &P = A.P;
+    int f1j = NEG, f2j = NEG, f1m = NEG, f2m = NEG;
+    for (int k = vi.beg + lane; k <= j - 1; k += 32) {
+        const int hk = hhat_cell<T>(A, S, vi, i, k, nbase, q, qlen, lg);
+        f1j = max(f1j, hk - P.oe1 - P.e1 * (j - 1 - k));
+        f2j = max(f2j, hk - P.oe2 - P.e2 * (j - 1 - k));
+        if (k <= j - 2) {
+            f1m = max(f1m, hk - P.oe1 - P.e1 * (j - 2 - k));
+            f2m = max(f2m, hk - P.oe2 - P.e2 * (j - 2 - k));
+        }
+    }
+    f[0] = __reduce_max_sync(FULL, f1j);
+    f[1] = __reduce_max_sync(FULL, f2j);
+    f[2] = __reduce_max_sync(FULL, f1m);
+    f[3] = __reduce_max_sync(FULL, f2m);
+}
+
+/* Writes qmap[t] = row the query base t is aligned to, -1 for an inserted base.  Returns false
+ * when no move is possible (abPOA dies in cg_backtrack; the reference then uses the first read). */
+template <typename T>
+__device__ __forceinline__ bool traceback(const KernelArgs &A, const Slot &S, const uint8_t *__restrict__ q, int qlen,
+                                          const AlnState &R, int lane) {
+    const DevParams &P = A.P;
+    const uint32_t *in_off = in_off_p(A, S), *in_row = in_row_p(A, S);
+    int32_t *qmap = qmap_p(A, S);
+    const int lg = R.lgpn;
+    int i = R.best_i, j = R.best_j, cur_op = OP_ALL;
+    for (int t = j + lane; t < qlen; t += 32) qmap[t] = -1;
+    while (i > 0 && j > 0) {
+        const RowView<T> vi = row_view<T>(A, S, i, lg, qlen);
+        const int in0 = (int)in_off[i], npre = (int)in_off[i + 1] - in0;
+        const int nbase = (int)(meta_p(A, S)[i] & META_BASE);
+        const int s = score_of(P, nbase, q[j - 1]);
+        const int hij = rv_get(vi, 0, j);
+        bool hit = false;
+        if (cur_op & OP_M) {
+            for (int k = 0; k < npre; ++k) {
+                const int p = (int)in_row[in0 + k];
+                const RowView<T> vp = row_view<T>(A, S, p, lg, qlen);
+                if (j - 1 < vp.beg || j - 1 > vp.end) continue;
+                if (rv_get(vp, 0, j - 1) + s == hij) {
+                    if (lane == 0) qmap[j - 1] = i;
+                    i = p; --j; hit = true; cur_op = OP_ALL;
+                    break;
+                }
+            }
+        }
+        if (!hit && (cur_op & OP_E)) {
+            for (int k = 0; k < npre && !hit; ++k) {
+                const int p = (int)in_row[in0 + k];
+                const RowView<T> vp = row_view<T>(A, S, p, lg, qlen);
+                if (j < vp.beg || j > vp.end) continue;
+                if (cur_op & OP_E1) {
+                    const int pe1 = rv_get(vp, 1, j);
+                    const bool take = (cur_op & OP_M) ? (hij == pe1) : (rv_get(vi, 1, j) == pe1 - P.e1);
+                    if (take) {
+                        cur_op = (rv_get(vp, 0, j) - P.oe1 == pe1) ? (OP_M | OP_F) : OP_E1;
+                        i = p; hit = true;
+                        break;
+                    }
+                }
+                if (cur_op & OP_E2) {
+                    const int pe2 = rv_get(vp, 2, j);
+                    const bool take = (cur_op & OP_M) ? (hij == pe2) : (rv_get(vi, 2, j) == pe2 - P.e2);
+                    if (take) {
+                        cur_op = (rv_get(vp, 0, j) - P.oe2 == pe2) ? (OP_M | OP_F) : OP_E2;
+                        i = p; hit = true;
+                        break;
+                    }
+                }
+            }
+        }
+        if (!hit && (cur_op & OP_F)) {
+            int f[4];
+            f_values<T>(A, S, vi, i, j, nbase, q, qlen, lg, lane, f);
+            const int hjm = rv_get(vi, 0, j - 1);
+            if (cur_op & OP_F1) {
+                if (!(cur_op & OP_M) || hij == f[0]) {
+                    if (hjm - P.oe1 == f[0]) { cur_op = OP_M | OP_E; hit = true; }
+                    else if (f[2] - P.e1 == f[0]) { cur_op = OP_F1; hit = true; }
+                }
+            }
+            if (!hit && (cur_op & OP_F2)) {
+                if (!(cur_op & OP_M) || hij == f[1]) {
+                    if (hjm - P.oe2 == f[1]) { cur_op = OP_M | OP_E; hit = true; }
+                    else if (f[3] - P.e2 == f[1]) { cur_op = OP_F2; hit = true; }
+                }
+            }
+            if (hit) {
+                if (lane == 0) qmap[j - 1] = -1;
+                --j;
+            }
+        }
+        if (!hit) return false;
+    }
+    for (int t = lane; t < j; t += 32) qmap[t] = -1;
+    __syncwarp();
+    return true;
+}
+
+}  // namespace mpoa

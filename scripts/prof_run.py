@@ -1,0 +1,22 @@
+"""Profiling driver: one resident batch, a few mpoa_batch_run passes (for ncu / launch lists)."""
+import sys
+import time
+
+sys.path.insert(0, ".")
+from mandalorion_b200 import PoaContext, pack_groups  # noqa: E402
+from mandalorion_b200.synth import make_groups  # noqa: E402
+
+cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+packed = pack_groups(make_groups(cfg, n))
+ctx = PoaContext(0)
+ctx.upload(*packed)
+for _ in range(reps):
+    t0 = time.time()
+    st = ctx.run()
+    print("run %.1f ms kernel %.1f ms  %.2f GCUPS  %.0f groups/s launches=%d" % (
+        (time.time() - t0) * 1e3, st["kernel_ms"], st["band_cells"] / st["kernel_ms"] / 1e6,
+        n / st["kernel_ms"] * 1e3, st["n_kernel_launches"]), st["phase_cycles"])
+out = ctx.fetch()
+print("ok groups", int((out["status"] == 0).sum()), "of", n)

@@ -85,7 +85,11 @@ def test_baseline_config_slices_match_oracle(gpu_ctx):
 def test_long_isoforms_int32_lanes(gpu_ctx):
     # cfg3: 5-12 kb reads, wide band; reads above 6546 nt take abPOA's int32 lane width (pn 8)
     got, want = both(gpu_ctx, make_groups("cfg3", 6))
-    assert got["stats"]["n_align_i32"] > 0 and got["stats"]["n_align_i16"] > 0
+    assert got["stats"]["n_align_i32"] > 0
+    # 5.5 kb reads stay in int16 lanes (5*qlen <= 32732) with a wide band
+    cfg = GroupConfig("p_long16", 3, 4, 6, 5400, 5600, "uniform", 0.01, (0.3, 0.35, 0.35))
+    got, want = both(gpu_ctx, make_groups(cfg))
+    assert got["stats"]["n_align_i16"] > 0 and got["stats"]["n_align_i32"] == 0
 
 
 def test_unrelated_reads_stress_band_edges(gpu_ctx):
