@@ -65,7 +65,9 @@ typedef struct mpoa_params {
     float   wf;
     int32_t simd_pn_i16;
     int32_t simd_pn_i32;
-    int32_t reserved[6];
+    int32_t debug_small_caps;  /* tests only: schedule the first attempt with deliberately too small
+                                  device workspaces / band capacity so the GPU retry paths run */
+    int32_t reserved[5];
 } mpoa_params;
 
 /* Work accounting of one batch call (all counters are sums over the batch). */

@@ -260,7 +260,7 @@ static SlotLayout make_layout(const Caps &c) {
         L.in_off[p] = take(n * 4); L.in_row[p] = take(e * 4);
         L.out_off[p] = take(n * 4); L.out_row[p] = take(e * 4); L.out_w[p] = take(e * 4);
     }
-    L.remain = take(n * 4); L.meta = take(n * 4); L.rowinfo = take(n * 16); L.rowtb = take(n * 8);
+    L.remain = take(n * 4); L.meta = take(n * 4); L.rowinfo = take(n * 16); L.rowtb = take(n * 16);
     L.rowbest = take(n * 4); L.qmap = take(q * 4);
     L.pv = take(q * 4); L.pkey = take(q * 4); L.pnew = take(q * 4); L.psib = take(q * 4);
     L.nin = take(q * 4); L.nout = take(q * 4);
@@ -354,7 +354,7 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
     std::iota(pending.begin(), pending.end(), 0);
     for (int64_t g = 0; g < ng; ++g) {
         GroupInfo &gi = ctx->ginfo[g];
-        gi.level = (int8_t)first_level(gi.lanes16 != 0, gi.wneed);
+        gi.level = (int8_t)first_level(gi.lanes16 != 0, ctx->params.debug_small_caps ? 1 : gi.wneed);
         gi.attempt = 0;
     }
     int64_t n_launch = 0;
@@ -391,7 +391,8 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
             for (int32_t g : gs) {
                 const GroupInfo &gi = ctx->ginfo[g];
                 uint64_t est;
-                if (gi.attempt == 0) est = (uint64_t)(gi.maxlen * (1.0 + 0.02 * gi.n_reads)) + 24ull * gi.n_reads + 256;
+                if (gi.attempt == 0 && ctx->params.debug_small_caps) est = (uint64_t)gi.maxlen + 8;
+                else if (gi.attempt == 0) est = (uint64_t)(gi.maxlen * (1.0 + 0.02 * gi.n_reads)) + 24ull * gi.n_reads + 256;
                 else if (gi.attempt == 1) est = (uint64_t)(gi.maxlen * (1.0 + 0.15 * gi.n_reads)) + 64ull * gi.n_reads + 1024;
                 else est = (uint64_t)gi.sumlen + 2;
                 est = std::min<uint64_t>(est, (uint64_t)gi.sumlen + 2);

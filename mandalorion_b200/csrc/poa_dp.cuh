@@ -16,7 +16,8 @@
  * quirk that the diagonal is not carried into the first cell of the overlap with a predecessor.
  *
  * Every row's H/Eout1/Eout2 go (a) into the shared-memory ring for the next rows and (b) to the
- * HBM traceback area: row r at rowtb[r].x (element offset), three arrays of rowtb[r].y elements.
+ * HBM traceback area: row r at rowtb[r].x (offset in 4-byte units), three arrays of rowtb[r].y
+ * elements; rowtb[r].z / .w keep the row's first predecessor and base for the traceback.
  */
 #pragma once
 #include "poa_graph.cuh"
@@ -106,7 +107,7 @@ __device__ __forceinline__ int dp_align32(const KernelArgs &A, const Slot &S, in
         if (lane == 0) {
             ring_info[0] = prev_info;
             rowinfo_p(A, S)[0] = prev_info;
-            rowtb_p(A, S)[0] = make_uint2(0, stride);
+            rowtb_p(A, S)[0] = make_uint4(0, stride, 0, 0);
         }
         tb_used = 3 * stride;
         __syncwarp();
@@ -173,7 +174,7 @@ __device__ __forceinline__ int dp_align32(const KernelArgs &A, const Slot &S, in
                     const int *Hp;
                     int pstride;
                     if (near) { Hp = ring + (p % RING) * 3 * wcap; pstride = wcap; }
-                    else { const uint2 rt = rowtb_p(A, S)[p]; Hp = tb + rt.x; pstride = (int)rt.y; }
+                    else { const uint4 rt = rowtb_p(A, S)[p]; Hp = tb + rt.x; pstride = (int)rt.y; }
                     const bool e_ok = cv && j >= lo && j <= hi;
                     if (e_ok) {
                         if (j > lo) mx = max(mx, Hp[j - 1 - pbeg]);
@@ -214,7 +215,7 @@ __device__ __forceinline__ int dp_align32(const KernelArgs &A, const Slot &S, in
             if (lane == 0) {
                 ring_info[i % RING] = prev_info;
                 rowinfo_p(A, S)[i] = prev_info;
-                rowtb_p(A, S)[i] = make_uint2(tbo, stride);
+                rowtb_p(A, S)[i] = make_uint4(tbo, stride, (uint32_t)p0, (uint32_t)nbase);
                 if (meta & META_TOSINK) rowbest_p(A, S)[i] = width > 0 ? last_h : NEG;
             }
             __syncwarp();
@@ -294,7 +295,7 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
         if (lane == 0) {
             ring_info[0] = prev_info;
             rowinfo_p(A, S)[0] = prev_info;
-            rowtb_p(A, S)[0] = make_uint2(0, 2 * stw);
+            rowtb_p(A, S)[0] = make_uint4(0, 2 * stw, 0, 0);
         }
         tb_used = 3 * stw;
         __syncwarp();
@@ -388,7 +389,7 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                         hl = hw;
                     }
                 } else {
-                    const uint2 rt = rowtb_p(A, S)[p];
+                    const uint4 rt = rowtb_p(A, S)[p];
                     const uint32_t *Hp = tb + rt.x;
                     const int pst = (int)(rt.y >> 1);
                     const int pwv = min(pw, pst);
@@ -516,7 +517,7 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
             if (lane == 0) {
                 ring_info[i % RING] = prev_info;
                 rowinfo_p(A, S)[i] = prev_info;
-                rowtb_p(A, S)[i] = make_uint2(tbo, 2 * stw);
+                rowtb_p(A, S)[i] = make_uint4(tbo, 2 * stw, (uint32_t)p0, (uint32_t)nbase);
             }
             if ((meta & META_TOSINK) && (width == 0 ? lane == 0 : (width - 1) / CPL == lane)) {
                 const int t = (width - 1) % CPL;

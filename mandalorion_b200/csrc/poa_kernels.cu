@@ -108,8 +108,8 @@ __device__ __forceinline__ int process_group(const KernelArgs &A, int slot, int 
         }
         __syncwarp();
         bool ok;
-        if constexpr (V == 0) ok = traceback<int32_t>(A, S, seq, len, R, lane);
-        else ok = traceback<int16_t>(A, S, seq, len, R, lane);
+        if constexpr (V == 0) ok = traceback<int32_t>(A, S, seq, len, R, lane, ring);
+        else ok = traceback<int16_t>(A, S, seq, len, R, lane, ring);
         __syncwarp();
         if (!ok) return ST_EMPTY;
         tk1 = clock64();

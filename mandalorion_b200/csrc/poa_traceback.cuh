@@ -16,6 +16,8 @@
 
 namespace mpoa {
 
+constexpr int TBW = 64;   // rows looked at by one speculative traceback batch
+
 enum TbOps { OP_M = 1, OP_E1 = 2, OP_E2 = 4, OP_E = 6, OP_F1 = 8, OP_F2 = 16, OP_F = 24, OP_ALL = 31 };
 
 template <typename T>
@@ -28,7 +30,7 @@ template <typename T>
 __device__ __forceinline__ RowView<T> row_view(const KernelArgs &A, const Slot &S, int r, int lg, int qlen) {
     RowView<T> v;
     const int4 info = rowinfo_p(A, S)[r];
-    const uint2 rt = rowtb_p(A, S)[r];
+    const uint4 rt = rowtb_p(A, S)[r];
     v.beg_sn = info.x; v.end_sn = info.y;
     v.beg = info.x << lg;
     v.end = ((info.y + 1) << lg) - 1;
@@ -94,14 +96,61 @@ __device__ __forceinline__ void f_values(const KernelArgs &A, const Slot &S, con
  * when no move is possible (abPOA dies in cg_backtrack; the reference then uses the first read). */
 template <typename T>
 __device__ __forceinline__ bool traceback(const KernelArgs &A, const Slot &S, const uint8_t *__restrict__ q, int qlen,
-                                          const AlnState &R, int lane) {
+                                          const AlnState &R, int lane, int *scratch) {
     const DevParams &P = A.P;
     const uint32_t *in_off = in_off_p(A, S), *in_row = in_row_p(A, S);
     int32_t *qmap = qmap_p(A, S);
     const int lg = R.lgpn;
     int i = R.best_i, j = R.best_j, cur_op = OP_ALL;
     for (int t = j + lane; t < qlen; t += 32) qmap[t] = -1;
+    int4 *winfo = reinterpret_cast<int4 *>(scratch);          // [TBW] rowinfo of rows i, i-1, ...
+    uint4 *wtb = reinterpret_cast<uint4 *>(scratch) + TBW;    // [TBW] rowtb
     while (i > 0 && j > 0) {
+        if (cur_op == OP_ALL) {
+            /*
+             * Speculative batch: in state ALL the next step is "diagonal to the FIRST predecessor"
+             * whenever H[p0][j-1] + s == H[i][j].  The chain i -> p0(i) -> p0(p0(i)) ... is followed
+             * for up to 31 steps, lane l checks step l against the stored rows, and the longest
+             * prefix of successful checks is taken at once.  Every step taken is exactly the step
+             * the serial logic below would have taken; a batch of length 0 falls through to it.
+             */
+            __syncwarp();
+            for (int x = lane; x < TBW; x += 32) {
+                const int row = i - x;
+                if (row >= 0) { winfo[x] = rowinfo_p(A, S)[row]; wtb[x] = rowtb_p(A, S)[row]; }
+            }
+            __syncwarp();
+            int x = 0, myx = lane == 0 ? 0 : -1;
+            for (int l = 1; l < 32; ++l) {
+                const int row = i - x;
+                const int nx = row > 0 ? i - (int)wtb[x].z : TBW;
+                if (nx >= TBW) break;
+                x = nx;
+                if (lane == l) myx = x;
+            }
+            const int col = j - lane;
+            bool inband = false;
+            int hval = NEG, row = -1, s = 0;
+            if (myx >= 0 && col >= 0) {
+                row = i - myx;
+                const int4 info = winfo[myx];
+                const uint4 rt = wtb[myx];
+                const int beg = info.x << lg, hi = min(((info.y + 1) << lg) - 1, qlen);
+                inband = col >= beg && col <= hi;
+                if (inband) hval = (int)reinterpret_cast<const T *>(reinterpret_cast<const uint32_t *>(tb_p(A, S)) + rt.x)[col - beg];
+                if (col >= 1) s = score_of(P, (int)rt.w, q[col - 1]);
+            }
+            const int hnext = __shfl_down_sync(FULL, hval, 1);
+            const bool nok = __shfl_down_sync(FULL, inband ? 1 : 0, 1) != 0;
+            const bool ok = lane < 31 && inband && row > 0 && col >= 1 && nok && (hnext + s == hval);
+            const int cnt = __ffs(~__ballot_sync(FULL, ok)) - 1;
+            if (cnt > 0) {
+                if (lane < cnt) qmap[col - 1] = row;
+                i = __shfl_sync(FULL, row, cnt);
+                j -= cnt;
+                continue;
+            }
+        }
         const RowView<T> vi = row_view<T>(A, S, i, lg, qlen);
         const int in0 = (int)in_off[i], npre = (int)in_off[i + 1] - in0;
         const int nbase = (int)(meta_p(A, S)[i] & META_BASE);

@@ -24,7 +24,8 @@ class PoaError(RuntimeError):
 class _Params(C.Structure):
     _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("gap_open1", C.c_int32), ("gap_ext1", C.c_int32),
                 ("gap_open2", C.c_int32), ("gap_ext2", C.c_int32), ("wb", C.c_int32), ("wf", C.c_float),
-                ("simd_pn_i16", C.c_int32), ("simd_pn_i32", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("simd_pn_i16", C.c_int32), ("simd_pn_i32", C.c_int32), ("debug_small_caps", C.c_int32),
+                ("reserved", C.c_int32 * 5)]
 
 
 class _Stats(C.Structure):
@@ -54,6 +55,7 @@ class PoaParams:
     wf: float = 0.01
     simd_pn_i16: int = 16
     simd_pn_i32: int = 8
+    debug_small_caps: int = 0      # tests only: force the GPU retry paths
 
 
 _lib = None
@@ -116,7 +118,7 @@ class PoaContext:
         lib = _load()
         p = params or PoaParams()
         cp = _Params(p.match, p.mismatch, p.gap_open1, p.gap_ext1, p.gap_open2, p.gap_ext2, p.wb, p.wf,
-                     p.simd_pn_i16, p.simd_pn_i32)
+                     p.simd_pn_i16, p.simd_pn_i32, p.debug_small_caps)
         h = C.c_void_p()
         rc = lib.mpoa_create(C.byref(h), int(device), C.byref(cp))
         if rc != 0:

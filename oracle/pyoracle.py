@@ -18,7 +18,8 @@ _LIB = os.path.join(_HERE, "libmpoa_oracle.so")
 class _Params(C.Structure):
     _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("gap_open1", C.c_int32), ("gap_ext1", C.c_int32),
                 ("gap_open2", C.c_int32), ("gap_ext2", C.c_int32), ("wb", C.c_int32), ("wf", C.c_float),
-                ("simd_pn_i16", C.c_int32), ("simd_pn_i32", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("simd_pn_i16", C.c_int32), ("simd_pn_i32", C.c_int32), ("debug_small_caps", C.c_int32),
+                ("reserved", C.c_int32 * 5)]
 
 
 class _Opts(C.Structure):

@@ -127,13 +127,18 @@ def test_golden_vectors(built):
         assert got["stats"]["band_cells"] == case["band_cells"]
 
 
-def test_capacity_retry_path_gives_the_same_answer(gpu_ctx):
-    # reads that share nothing make the graph grow to sum(len): the first-attempt workspace
-    # estimate overflows and the group is re-run on the GPU with a larger workspace
-    rng = np.random.default_rng(11)
-    groups = [[random_seq(rng, 300) for _ in range(30)] for _ in range(3)] + make_groups("cfg1", 4)
-    got, _ = both(gpu_ctx, groups)
-    assert got["stats"]["n_retry_groups"] >= 1
+def test_retry_paths_give_the_same_answer(built):
+    # debug_small_caps schedules the first attempt with a workspace sized for the first read only
+    # and the narrowest kernel variant: groups overflow (node capacity / band width / int16 lanes)
+    # and are re-run ON THE GPU with larger capacities or a wider variant -- never on the CPU
+    groups = make_groups("cfg1", 12) + make_groups("cfg3", 1) + make_groups("cfg4", 1)
+    packed = pack_groups(groups)
+    want = oracle_consensus_batch(packed=packed, trace=True, n_threads=os.cpu_count() or 1)
+    with PoaContext(0, PoaParams(debug_small_caps=1)) as ctx:
+        got = ctx.consensus_batch(packed=packed, trace=True)
+    assert_same(got, want, packed)
+    assert got["stats"]["n_retry_groups"] >= len(groups) - 1
+    assert got["stats"]["n_kernel_launches"] >= 2
 
 
 def test_properties_at_scale(gpu_ctx):
