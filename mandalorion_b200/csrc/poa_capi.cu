@@ -62,6 +62,8 @@ struct mpoa_ctx {
     uint8_t *d_ws = nullptr;
     size_t ws_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t side[16] = {nullptr};
+    cudaEvent_t fork_ev = nullptr, join_ev[16] = {nullptr};
     double h2d_ms = 0;
     bool ran = false;
     std::vector<int32_t> h_status;
@@ -117,7 +119,7 @@ extern "C" int mpoa_create(mpoa_ctx **out, int device_ordinal, const mpoa_params
     if (p) ctx->params = *p; else mpoa_default_params(&ctx->params);
     if (ctx->params.simd_pn_i16 <= 0) ctx->params.simd_pn_i16 = 16;
     if (ctx->params.simd_pn_i32 <= 0) ctx->params.simd_pn_i32 = 8;
-    if (cudaMalloc(&ctx->d_queue_head, sizeof(int)) != cudaSuccess ||
+    if (cudaMalloc(&ctx->d_queue_head, 16 * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&ctx->d_stats, SI_COUNT * sizeof(unsigned long long)) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
         delete ctx;
@@ -136,6 +138,11 @@ extern "C" void mpoa_destroy(mpoa_ctx *ctx) {
     cudaFree(ctx->d_stats);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    for (int k = 0; k < 16; ++k) {
+        if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
+        if (ctx->join_ev[k]) cudaEventDestroy(ctx->join_ev[k]);
+    }
     delete ctx;
 }
 
@@ -188,7 +195,8 @@ extern "C" int mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups, const int64_t 
         if (gi.n_reads == 0) gi.minlen = 0;
         /* expected band: 2w + length spread + SIMD rounding on both sides + slack */
         const int w = ctx->params.wb + (int)(ctx->params.wf * (float)gi.maxlen);
-        gi.wneed = 2 * w + (gi.maxlen - gi.minlen) + 2 * ctx->params.simd_pn_i16 + 48;
+        /* widest row seen on calibration sets: 2w+1 + length spread + two SIMD vectors of rounding */
+        gi.wneed = 2 * w + 1 + (gi.maxlen - gi.minlen) + 2 * ctx->params.simd_pn_i16 + 4;
         gi.wneed = std::min(gi.wneed, gi.maxlen + 1 + 2 * ctx->params.simd_pn_i16);
         gi.cost = (double)gi.sumlen * (double)gi.wneed;
         /* abPOA's own rule for int16 lanes (scores and gap-extended lengths below 32767 minus slack) */
@@ -274,7 +282,7 @@ static SlotLayout make_layout(const Caps &c) {
  * band capacity in cells.  A group escalates along this list when its band or scores outgrow
  * the level it was scheduled at. */
 struct Level { int variant, wcap; };
-static const Level kLevels[] = {{2, 128}, {4, 256}, {8, 512}, {0, 256}, {0, 512}, {0, 1024}, {0, 2048}, {0, 4096},
+static const Level kLevels[] = {{2, 128}, {3, 192}, {4, 256}, {8, 512}, {0, 256}, {0, 512}, {0, 1024}, {0, 2048}, {0, 4096},
                                 {0, 8192}, {0, 16384}};
 static const int kNumLevels = (int)(sizeof(kLevels) / sizeof(kLevels[0]));
 
@@ -288,39 +296,24 @@ static bool level_covers(int b, int a, bool lanes16) {
     return kLevels[b].wcap >= kLevels[a].wcap && (kLevels[b].variant == 0 || lanes16);
 }
 
-/* run one set of groups with one set of capacities; appends groups that need more to `retry` */
-static int run_launch(mpoa_ctx *ctx, const std::vector<int32_t> &groups, const Caps &caps, int64_t *n_launch) {
-    if (groups.empty()) return MPOA_OK;
-    /* warps per block: as many (<=4) as the shared-memory ring allows */
-    int wpb = 4;
-    while (wpb > 1 && poa_smem_bytes(caps.variant, caps.wcap, wpb) > ctx->smem_optin) wpb >>= 1;
-    if (poa_smem_bytes(caps.variant, caps.wcap, wpb) > ctx->smem_optin) { ctx->err = "band wider than shared memory allows"; return 1; }
-    int bps = poa_max_blocks_per_sm(caps.variant, caps.wcap, wpb);
-    if (bps <= 0) { ctx->err = "kernel cannot be resident (shared memory)"; return MPOA_ECUDA; }
-    const SlotLayout L = make_layout(caps);
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
-    const uint64_t avail = (uint64_t)free_b + ctx->ws_bytes;
-    int64_t n_blocks = (int64_t)bps * ctx->n_sm;
-    const int64_t need_blocks = ((int64_t)groups.size() + wpb - 1) / wpb;
-    n_blocks = std::min(n_blocks, need_blocks);
-    const uint64_t budget = (uint64_t)(avail * 0.85);
-    if ((uint64_t)n_blocks * wpb * L.slot_bytes > budget) n_blocks = (int64_t)(budget / ((uint64_t)wpb * L.slot_bytes));
-    if (n_blocks <= 0) { ctx->err = "not enough device memory for one workspace slot"; return 1; }
-    const uint64_t need = (uint64_t)n_blocks * wpb * L.slot_bytes;
-    if (need > ctx->ws_bytes) {
-        cudaFree(ctx->d_ws);
-        ctx->d_ws = nullptr; ctx->ws_bytes = 0;
-        CK(cudaMalloc(&ctx->d_ws, need));
-        ctx->ws_bytes = need;
-    }
-    CK(cudaMemcpyAsync(ctx->d_queue, groups.data(), groups.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_queue_head, 0, sizeof(int), ctx->stream));
-    KernelArgs A;
+/* one kernel launch of a round: the groups of one level with one set of capacities */
+struct Launch {
+    int lv = 0;
+    std::vector<int32_t> gs;
+    Caps c;
+    SlotLayout L;
+    int wpb = 4, bps = 0;
+    int64_t n_blocks = 0;
+    double cost = 0;
+    uint64_t ws_off = 0;
+    size_t q_off = 0;
+};
+
+static void fill_args(mpoa_ctx *ctx, const Launch &ln, int k, KernelArgs &A) {
     std::memset(&A, 0, sizeof(A));
     A.codes = ctx->d_codes; A.read_off = ctx->d_rbo; A.group_read_off = ctx->d_gro;
-    A.queue = ctx->d_queue; A.n_queue = (int)groups.size(); A.queue_head = ctx->d_queue_head;
-    A.ws = ctx->d_ws; A.L = L;
+    A.queue = ctx->d_queue + ln.q_off; A.n_queue = (int)ln.gs.size(); A.queue_head = ctx->d_queue_head + k;
+    A.ws = ctx->d_ws + ln.ws_off; A.L = ln.L;
     A.cons = ctx->d_cons; A.cons_off = ctx->d_region_off; A.cons_len = ctx->d_cons_len; A.status = ctx->d_status;
     A.stats = ctx->d_stats;
     A.tr_score = ctx->d_tr_score; A.tr_bits = ctx->d_tr_bits; A.tr_cells = ctx->d_tr_cells;
@@ -330,9 +323,109 @@ static int run_launch(mpoa_ctx *ctx, const std::vector<int32_t> &groups, const C
     A.P.o1 = p.gap_open1; A.P.e1 = p.gap_ext1; A.P.o2 = p.gap_open2; A.P.e2 = p.gap_ext2;
     A.P.oe1 = p.gap_open1 + p.gap_ext1; A.P.oe2 = p.gap_open2 + p.gap_ext2;
     A.P.wb = p.wb; A.P.wf = p.wf; A.P.pn16 = p.simd_pn_i16; A.P.pn32 = p.simd_pn_i32;
-    A.wcap = caps.wcap;
-    CK(launch_poa(caps.variant, A, (int)n_blocks, wpb, ctx->stream));
-    ++*n_launch;
+    A.wcap = ln.c.wcap;
+    auto p2 = [](int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); };
+    const int cpl = 2 * std::max(1, ln.c.variant);
+    A.K.neg2 = p2(NEG16, NEG16);
+    A.K.noe = p2(-A.P.oe1, -A.P.oe2); A.K.nee = p2(-A.P.e1, -A.P.e2);
+    A.K.noe1 = p2(-A.P.oe1, -A.P.oe1); A.K.noe2 = p2(-A.P.oe2, -A.P.oe2);
+    A.K.ne1 = p2(-A.P.e1, -A.P.e1); A.K.ne2 = p2(-A.P.e2, -A.P.e2);
+    A.K.match2 = p2(A.P.match, A.P.match); A.K.mism2 = p2(-A.P.mismatch, -A.P.mismatch);
+    for (int d = 0; d < 5; ++d) A.K.dec[d] = p2(-A.P.e1 * cpl * (1 << d), -A.P.e2 * cpl * (1 << d));
+}
+
+/*
+ * Runs the launches of one round CONCURRENTLY (one stream each): every level gets a share of
+ * the resident warps proportional to its estimated cost, so a level with few groups neither
+ * waits for the others nor holds the whole GPU.  Groups that cannot be launched at all get
+ * ST_EMPTY in h_status.
+ */
+static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_launch) {
+    std::vector<Launch *> live;
+    double tot_cost = 0;
+    for (Launch &ln : launches) {
+        ln.wpb = 4;
+        while (ln.wpb > 1 && poa_smem_bytes(ln.c.variant, ln.c.wcap, ln.wpb) > ctx->smem_optin) ln.wpb >>= 1;
+        ln.bps = poa_smem_bytes(ln.c.variant, ln.c.wcap, ln.wpb) > ctx->smem_optin
+                     ? 0 : poa_max_blocks_per_sm(ln.c.variant, ln.c.wcap, ln.wpb);
+        if (ln.bps <= 0) {
+            ctx->err = "band wider than shared memory allows";
+            for (int32_t g : ln.gs) ctx->h_status[g] = ST_EMPTY;
+            continue;
+        }
+        ln.L = make_layout(ln.c);
+        ln.cost = 0;
+        for (int32_t g : ln.gs) ln.cost += ctx->ginfo[g].cost;
+        tot_cost += ln.cost;
+        live.push_back(&ln);
+    }
+    if (live.empty()) return MPOA_OK;
+    if (live.size() > 16) { ctx->err = "too many launch levels"; return MPOA_EINVAL; }
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t budget = (uint64_t)(((uint64_t)free_b + ctx->ws_bytes) * 0.85);
+    uint64_t need = 0;
+    for (Launch *ln : live) {
+        const double share = live.size() == 1 ? 1.0 : std::max(ln->cost / std::max(tot_cost, 1.0), 0.02);
+        int64_t nb = (int64_t)std::max(1.0, share * ln->bps * ctx->n_sm + 0.5);
+        nb = std::min<int64_t>(nb, ((int64_t)ln->gs.size() + ln->wpb - 1) / ln->wpb);
+        ln->n_blocks = nb;
+        need += (uint64_t)nb * ln->wpb * ln->L.slot_bytes;
+    }
+    if (need > budget) {
+        const double f = (double)budget / (double)need;
+        need = 0;
+        for (Launch *ln : live) {
+            ln->n_blocks = (int64_t)(ln->n_blocks * f);
+            if (ln->n_blocks <= 0 && (uint64_t)ln->wpb * ln->L.slot_bytes <= budget / live.size()) ln->n_blocks = 1;
+            need += (uint64_t)ln->n_blocks * ln->wpb * ln->L.slot_bytes;
+        }
+    }
+    if (need > ctx->ws_bytes) {
+        cudaFree(ctx->d_ws);
+        ctx->d_ws = nullptr; ctx->ws_bytes = 0;
+        CK(cudaMalloc(&ctx->d_ws, need));
+        ctx->ws_bytes = need;
+    }
+    uint64_t ws_off = 0;
+    size_t q_off = 0;
+    std::vector<int32_t> hq;
+    for (Launch *ln : live) {
+        ln->ws_off = ws_off; ln->q_off = q_off;
+        ws_off += (uint64_t)ln->n_blocks * ln->wpb * ln->L.slot_bytes;
+        q_off += ln->gs.size();
+        hq.insert(hq.end(), ln->gs.begin(), ln->gs.end());
+    }
+    CK(cudaMemcpyAsync(ctx->d_queue, hq.data(), hq.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_queue_head, 0, 16 * sizeof(int), ctx->stream));
+    const bool fork = live.size() > 1;
+    if (fork) {
+        if (!ctx->fork_ev) CK(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+        CK(cudaEventRecord(ctx->fork_ev, ctx->stream));
+    }
+    for (size_t k = 0; k < live.size(); ++k) {
+        Launch *ln = live[k];
+        if (ln->n_blocks <= 0) {
+            ctx->err = "not enough device memory for one workspace slot";
+            for (int32_t g : ln->gs) ctx->h_status[g] = ST_EMPTY;
+            continue;
+        }
+        cudaStream_t st = ctx->stream;
+        if (fork) {
+            if (!ctx->side[k]) CK(cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking));
+            if (!ctx->join_ev[k]) CK(cudaEventCreateWithFlags(&ctx->join_ev[k], cudaEventDisableTiming));
+            st = ctx->side[k];
+            CK(cudaStreamWaitEvent(st, ctx->fork_ev, 0));
+        }
+        KernelArgs A;
+        fill_args(ctx, *ln, (int)k, A);
+        CK(launch_poa(ln->c.variant, A, (int)ln->n_blocks, ln->wpb, st));
+        ++*n_launch;
+        if (fork) {
+            CK(cudaEventRecord(ctx->join_ev[k], st));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->join_ev[k], 0));
+        }
+    }
     return MPOA_OK;
 }
 
@@ -364,7 +457,7 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
          * wider level that covers it (launches of one batch are serialised) */
         std::vector<std::vector<int32_t>> bins(kNumLevels);
         for (int32_t g : pending) bins[ctx->ginfo[g].level].push_back(g);
-        const size_t min_groups = (size_t)ctx->n_sm * 8;
+        const size_t min_groups = (size_t)ctx->n_sm;
         for (int a = 0; a < kNumLevels; ++a) {
             if (bins[a].empty() || bins[a].size() >= min_groups) continue;
             bool all16 = true;
@@ -376,6 +469,7 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
                 break;
             }
         }
+        std::vector<Launch> launches;
         for (int lv = 0; lv < kNumLevels; ++lv) {
             auto &gs = bins[lv];
             if (gs.empty()) continue;
@@ -409,11 +503,14 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
                                                   0x7fffff00u);
             c.qcap = (uint32_t)qcap + 8;
             c.tbcap = std::min<uint64_t>(tbmax + 4096, 0x3fff00000ull);
-            int rc = run_launch(ctx, gs, c, &n_launch);
+            launches.emplace_back();
+            launches.back().lv = lv;
+            launches.back().gs = gs;
+            launches.back().c = c;
+        }
+        {
+            const int rc = run_round(ctx, launches, &n_launch);
             if (rc < 0) return rc;
-            if (rc > 0) {  // cannot be run with these capacities at all: treated like an abpoa failure
-                for (int32_t g : gs) ctx->h_status[g] = ST_EMPTY;
-            }
         }
         CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaMemcpy(dstat.data(), ctx->d_status, ng * sizeof(int32_t), cudaMemcpyDeviceToHost));

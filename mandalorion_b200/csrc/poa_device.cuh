@@ -40,6 +40,17 @@ struct DevParams {
     int pn16, pn32;
 };
 
+/* int16x2 constants of the packed DP, built once on the host (they sit in the constant bank and
+ * are used directly as instruction operands).  (a,b) = a in the low half, b in the high half. */
+struct Packed16 {
+    uint32_t neg2;             // (NEG16, NEG16)
+    uint32_t noe, nee;         // (-oe1,-oe2), (-e1,-e2): per-cell words holding (F1,F2)
+    uint32_t noe1, noe2;       // (-oe1,-oe1), (-oe2,-oe2): per-word of two cells
+    uint32_t ne1, ne2;         // (-e1,-e1), (-e2,-e2)
+    uint32_t match2, mism2;    // (match,match), (-mismatch,-mismatch)
+    uint32_t dec[5];           // decay of the cross-lane F scan at distance 1,2,4,8,16 lanes
+};
+
 /* byte offsets of the arrays inside one warp's HBM workspace ("slot") */
 struct SlotLayout {
     uint32_t ncap, ecap, qcap;
@@ -70,6 +81,7 @@ struct KernelArgs {
     long long *tr_cells;
     int32_t *tr_aln, *tr_node;
     DevParams P;
+    Packed16 K;
     int wcap;                        // cells per ring row
 };
 
@@ -77,7 +89,7 @@ enum StatIdx { SI_CELLS = 0, SI_INTOPS, SI_FULL, SI_ALN, SI_ALN16, SI_ALN32, SI_
                SI_T_PREP, SI_T_DP, SI_T_TB, SI_T_MERGE, SI_T_CONS, SI_T_BUSY, SI_COUNT };
 
 /* kernel variants: 0 = int32 lanes, any band width (chunks of 32 cells);
- * 2/4/8 = packed int16x2, that many 32-bit words (pairs of cells) per lane: band <= 128/256/512 */
-constexpr int kVariants[] = {0, 2, 4, 8};
+ * 2/3/4/8 = packed int16x2, that many 32-bit words (pairs of cells) per lane: band <= 128/192/256/512 */
+constexpr int kVariants[] = {0, 2, 3, 4, 8};
 
 }  // namespace mpoa

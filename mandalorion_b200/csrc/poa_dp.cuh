@@ -29,6 +29,15 @@ struct AlnState {
     unsigned long long cells, intops, full, tbbytes;
 };
 
+/* per-alignment work counters kept in 32 bits inside the row loop */
+struct RowCount {
+    uint32_t cells, extra, rows;
+    __device__ __forceinline__ void add(int width, int npre) { cells += width; extra += (uint32_t)max(0, npre - 1) * width; ++rows; }
+    __device__ __forceinline__ void flush(AlnState &R, int qlen) const {
+        R.cells = cells; R.intops = 17ull * cells + 3ull * extra; R.full = (unsigned long long)rows * (qlen + 1);
+    }
+};
+
 /* lane width abPOA would have used (decides the SIMD vector length the band is rounded to) */
 __device__ __forceinline__ void lane_width_rule(const DevParams &P, int qlen, int N, AlnState &R) {
     const int len = max(qlen, N);
@@ -83,7 +92,7 @@ __device__ __forceinline__ int dp_align32(const KernelArgs &A, const Slot &S, in
     const int lg = R.lgpn;
     const int w = P.wb < 0 ? qlen : P.wb + (int)__fmul_rn(P.wf, (float)qlen);
     uint32_t tb_used = 0;
-    R.cells = R.intops = R.full = 0;
+    RowCount RC = {0, 0, 0};
 
     /* row 0: the source */
     int4 prev_info;
@@ -135,14 +144,21 @@ __device__ __forceinline__ int dp_align32(const KernelArgs &A, const Slot &S, in
             const int p0 = __shfl_sync(FULL, m_p0, l);
             const int nbase = meta & META_BASE;
 
+            /* most rows have ONE predecessor and it is the previous row: straight-line path */
+            const bool simple = npre == 1 && p0 == i - 1;
             int left = N, right = 0, minb = INT_MAX, maxe = -1;
-            for (int k = 0; k < npre; ++k) {
-                const int p = k == 0 ? p0 : (int)in_row[in0 + k];
-                const int4 pi = (p == i - 1) ? prev_info : ((i - p < RING) ? ring_info[p % RING] : rowinfo_p(A, S)[p]);
-                left = min(left, pi.z + 1);
-                right = max(right, pi.w + 1);
-                minb = min(minb, pi.x);
-                maxe = max(maxe, pi.y);
+            if (simple) {
+                left = min(N, prev_info.z + 1); right = max(0, prev_info.w + 1);
+                minb = prev_info.x; maxe = prev_info.y;
+            } else {
+                for (int k = 0; k < npre; ++k) {
+                    const int p = k == 0 ? p0 : (int)in_row[in0 + k];
+                    const int4 pi = (p == i - 1) ? prev_info : ((i - p < RING) ? ring_info[p & (RING - 1)] : rowinfo_p(A, S)[p]);
+                    left = min(left, pi.z + 1);
+                    right = max(right, pi.w + 1);
+                    minb = min(minb, pi.x);
+                    maxe = max(maxe, pi.y);
+                }
             }
             const Band B = make_band(left, right, minb, maxe, rem, qlen, w, lg);
             const int width = B.width, dp_beg = B.dp_beg, beg_sn = B.beg_sn, end_sn = B.end_sn;
@@ -151,9 +167,7 @@ __device__ __forceinline__ int dp_align32(const KernelArgs &A, const Slot &S, in
             const uint32_t tbo = tb_used;
             if ((uint64_t)tb_used + 3ull * stride > tbcap) return ST_RETRY;
             tb_used += 3 * stride;
-            R.cells += width;
-            R.intops += 17ull * width + 3ull * (unsigned)max(0, npre - 1) * width;
-            R.full += qlen + 1;
+            RC.add(width, npre);
 
             int *Hr = ring + (i % RING) * 3 * wcap, *E1r = Hr + wcap, *E2r = Hr + 2 * wcap;
             int carry_s1 = NEG - P.oe1, carry_s2 = NEG - P.oe2;
@@ -222,6 +236,7 @@ __device__ __forceinline__ int dp_align32(const KernelArgs &A, const Slot &S, in
         }
     }
     R.tbbytes = (unsigned long long)tb_used * 4;
+    RC.flush(R, qlen);
     pick_best(A, S, N, qlen, R);
     return ST_OK;
 }
@@ -249,19 +264,23 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
     const DevParams &P = A.P;
     const uint32_t *in_off = in_off_p(A, S), *in_row = in_row_p(A, S);
     uint32_t *tb = reinterpret_cast<uint32_t *>(tb_p(A, S));   // words = pairs of int16 cells
-    const uint64_t tbcap = A.L.tbcap / 4;
+    const uint32_t tbcap = (uint32_t)min(A.L.tbcap / 4, (uint64_t)0xfffffff0u);
     lane_width_rule(P, qlen, N, R);
     if (R.bits != 16) return ST_RETRY_32;     // needs the int32 kernel
     const int lg = R.lgpn;
     const int w = P.wb < 0 ? qlen : P.wb + (int)__fmul_rn(P.wf, (float)qlen);
     uint32_t tb_used = 0;                     // words
-    R.cells = R.intops = R.full = 0;
+    RowCount RC = {0, 0, 0};
 
+    const Packed16 &K = A.K;
     const uint32_t NEG2 = pack2(NEG16, NEG16);
-    const uint32_t NOE = pack2(-P.oe1, -P.oe2), NEE = pack2(-P.e1, -P.e2);           // (gap1, gap2) per cell
-    const uint32_t NOE1 = pack2(-P.oe1, -P.oe1), NOE2 = pack2(-P.oe2, -P.oe2);       // per word of two cells
-    const uint32_t NE1 = pack2(-P.e1, -P.e1), NE2 = pack2(-P.e2, -P.e2);
-    const uint32_t MATCH2 = pack2(P.match, P.match), MISM2 = pack2(-P.mismatch, -P.mismatch);
+#define NEE K.nee
+#define NOE1 K.noe1
+#define NOE2 K.noe2
+#define NE1 K.ne1
+#define NE2 K.ne2
+#define MATCH2 K.match2
+#define MISM2 K.mism2
     const int wl0 = lane * WPL;               // first word of this lane inside a row
     const int col0 = lane * CPL;              // first cell
 
@@ -275,7 +294,7 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
         const int width = hi + 1;
         if (width > WCAP) return ST_RETRY_WIDE;
         const uint32_t stw = (uint32_t)(((width + 1) >> 1) + WPL - 1) / WPL * WPL;   // stored words per array
-        if ((uint64_t)3 * stw > tbcap) return ST_RETRY;
+        if (3 * stw > tbcap) return ST_RETRY;
         uint32_t *Hs = ring + RING_PAD, *E1s = Hs + RW, *E2s = Hs + 2 * RW;
 #pragma unroll
         for (int m = 0; m < WPL; ++m) {
@@ -326,25 +345,30 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
             const int p0 = __shfl_sync(FULL, m_p0, l);
             const int nbase = meta & META_BASE;
 
+            /* most rows have ONE predecessor and it is the previous row: straight-line path */
+            const bool simple = npre == 1 && p0 == i - 1;
             int left = N, right = 0, minb = INT_MAX, maxe = -1;
-            for (int k = 0; k < npre; ++k) {
-                const int p = k == 0 ? p0 : (int)in_row[in0 + k];
-                const int4 pi = (p == i - 1) ? prev_info : ((i - p < RING) ? ring_info[p % RING] : rowinfo_p(A, S)[p]);
-                left = min(left, pi.z + 1);
-                right = max(right, pi.w + 1);
-                minb = min(minb, pi.x);
-                maxe = max(maxe, pi.y);
+            if (simple) {
+                left = min(N, prev_info.z + 1); right = max(0, prev_info.w + 1);
+                minb = prev_info.x; maxe = prev_info.y;
+            } else {
+                for (int k = 0; k < npre; ++k) {
+                    const int p = k == 0 ? p0 : (int)in_row[in0 + k];
+                    const int4 pi = (p == i - 1) ? prev_info : ((i - p < RING) ? ring_info[p & (RING - 1)] : rowinfo_p(A, S)[p]);
+                    left = min(left, pi.z + 1);
+                    right = max(right, pi.w + 1);
+                    minb = min(minb, pi.x);
+                    maxe = max(maxe, pi.y);
+                }
             }
             const Band B = make_band(left, right, minb, maxe, rem, qlen, w, lg);
             const int width = B.width, dp_beg = B.dp_beg;
             if (width > WCAP) return ST_RETRY_WIDE;
             const uint32_t stw = (uint32_t)(((width + 1) >> 1) + WPL - 1) / WPL * WPL;
             const uint32_t tbo = tb_used;
-            if ((uint64_t)tb_used + 3ull * stw > tbcap) return ST_RETRY;
+            if (tbcap - tb_used < 3 * stw) return ST_RETRY;
             tb_used += 3 * stw;
-            R.cells += width;
-            R.intops += 17ull * width + 3ull * (unsigned)max(0, npre - 1) * width;
-            R.full += qlen + 1;
+            RC.add(width, npre);
 
             /* query bases under this lane's cells: q[j-1], j = dp_beg + col0 + t; reloaded only
              * when the band start moves (every ~pn rows) */
@@ -366,45 +390,37 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
             uint32_t M2[WPL], EA[WPL], EB[WPL];
 #pragma unroll
             for (int m = 0; m < WPL; ++m) { M2[m] = NEG2; EA[m] = NEG2; EB[m] = NEG2; }
-            for (int k = 0; k < npre; ++k) {
-                const int p = k == 0 ? p0 : (int)in_row[in0 + k];
-                const bool near = i - p < RING;
-                const int4 pi = (p == i - 1) ? prev_info : (near ? ring_info[p % RING] : rowinfo_p(A, S)[p]);
-                const int pw = ((pi.y - pi.x + 1) << lg) >> 1;                 // words of the pred's rounded band
-                const int shw = (dp_beg - (pi.x << lg)) >> 1;                  // our word 0 = pred word shw
+            auto gather = [&](const uint32_t *Hp, int st, int pw, int shw) {
                 const int wp0 = wl0 + shw;
-                if (near) {
-                    const uint32_t *Hp = ring + (p % RING) * 3 * RW + RING_PAD;
-                    uint32_t hl = ((unsigned)(wp0 - 1) < (unsigned)pw) ? Hp[wp0 - 1] : NEG2;
+                uint32_t hl = ((unsigned)(wp0 - 1) < (unsigned)pw) ? Hp[wp0 - 1] : NEG2;
 #pragma unroll
-                    for (int m = 0; m < WPL; ++m) {
-                        const int wp = wp0 + m;
-                        const bool v = (unsigned)wp < (unsigned)pw;
-                        const uint32_t hw = v ? Hp[wp] : NEG2;
-                        const uint32_t e1w = v ? Hp[RW + wp] : NEG2, e2w = v ? Hp[2 * RW + wp] : NEG2;
-                        const uint32_t dg = v ? __byte_perm(hl, hw, 0x5432) : NEG2;
-                        M2[m] = __vmaxs2(M2[m], dg);
-                        EA[m] = __vmaxs2(EA[m], e1w);
-                        EB[m] = __vmaxs2(EB[m], e2w);
-                        hl = hw;
-                    }
-                } else {
-                    const uint4 rt = rowtb_p(A, S)[p];
-                    const uint32_t *Hp = tb + rt.x;
-                    const int pst = (int)(rt.y >> 1);
-                    const int pwv = min(pw, pst);
-                    uint32_t hl = ((unsigned)(wp0 - 1) < (unsigned)pwv) ? Hp[wp0 - 1] : NEG2;
-#pragma unroll
-                    for (int m = 0; m < WPL; ++m) {
-                        const int wp = wp0 + m;
-                        const bool v = (unsigned)wp < (unsigned)pwv;
-                        const uint32_t hw = v ? Hp[wp] : NEG2;
-                        const uint32_t e1w = v ? Hp[pst + wp] : NEG2, e2w = v ? Hp[2 * pst + wp] : NEG2;
-                        const uint32_t dg = v ? __byte_perm(hl, hw, 0x5432) : NEG2;
-                        M2[m] = __vmaxs2(M2[m], dg);
-                        EA[m] = __vmaxs2(EA[m], e1w);
-                        EB[m] = __vmaxs2(EB[m], e2w);
-                        hl = hw;
+                for (int m = 0; m < WPL; ++m) {
+                    const int wp = wp0 + m;
+                    const bool v = (unsigned)wp < (unsigned)pw;
+                    const uint32_t hw = v ? Hp[wp] : NEG2;
+                    const uint32_t e1w = v ? Hp[st + wp] : NEG2, e2w = v ? Hp[2 * st + wp] : NEG2;
+                    const uint32_t dg = v ? __byte_perm(hl, hw, 0x5432) : NEG2;
+                    M2[m] = __vmaxs2(M2[m], dg);
+                    EA[m] = __vmaxs2(EA[m], e1w);
+                    EB[m] = __vmaxs2(EB[m], e2w);
+                    hl = hw;
+                }
+            };
+            if (simple) {
+                gather(ring + ((i - 1) & (RING - 1)) * 3 * RW + RING_PAD, RW,
+                       ((prev_info.y - prev_info.x + 1) << lg) >> 1, (dp_beg - (prev_info.x << lg)) >> 1);
+            } else {
+                for (int k = 0; k < npre; ++k) {
+                    const int p = k == 0 ? p0 : (int)in_row[in0 + k];
+                    const bool near = i - p < RING;
+                    const int4 pi = (p == i - 1) ? prev_info : (near ? ring_info[p & (RING - 1)] : rowinfo_p(A, S)[p]);
+                    const int pw = ((pi.y - pi.x + 1) << lg) >> 1;             // words of the pred's rounded band
+                    const int shw = (dp_beg - (pi.x << lg)) >> 1;              // our word 0 = pred word shw
+                    if (near) gather(ring + (p & (RING - 1)) * 3 * RW + RING_PAD, RW, pw, shw);
+                    else {
+                        const uint4 rt = rowtb_p(A, S)[p];
+                        const int pst = (int)(rt.y >> 1);
+                        gather(tb + rt.x, pst, min(pw, pst), shw);
                     }
                 }
             }
@@ -444,10 +460,9 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
             for (int t = 1; t < CPL; ++t) FL[t] = __viaddmax_s16x2(FL[t - 1], NEE, X[t - 1]);
             uint32_t T = __viaddmax_s16x2(FL[CPL - 1], NEE, X[CPL - 1]);
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t up = __shfl_up_sync(FULL, T, d);
-                const uint32_t dec = pack2(-P.e1 * CPL * d, -P.e2 * CPL * d);
-                T = __viaddmax_s16x2(up, dec, T);
+            for (int dd = 0; dd < 5; ++dd) {
+                const uint32_t up = __shfl_up_sync(FULL, T, 1 << dd);
+                T = __viaddmax_s16x2(up, K.dec[dd], T);
             }
             uint32_t C = __shfl_up_sync(FULL, T, 1);
             if (lane == 0) C = NEG2;
@@ -475,7 +490,7 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
 
             /* ring + HBM stores */
             {
-                uint32_t *Hr = ring + (i % RING) * 3 * RW + RING_PAD;
+                uint32_t *Hr = ring + (i & (RING - 1)) * 3 * RW + RING_PAD;
                 const bool st = (uint32_t)wl0 < stw;
 #pragma unroll
                 for (int m = 0; m < WPL; ++m) {
@@ -483,7 +498,10 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                 }
                 if (st) {
                     uint32_t *g = tb + tbo + wl0;
-                    if constexpr (WPL == 2) {
+                    if constexpr (WPL == 3) {
+#pragma unroll
+                        for (int m = 0; m < WPL; ++m) { g[m] = Hw[m]; g[stw + m] = E1o[m]; g[2 * stw + m] = E2o[m]; }
+                    } else if constexpr (WPL == 2) {
                         *reinterpret_cast<uint2 *>(g) = make_uint2(Hw[0], Hw[1]);
                         *reinterpret_cast<uint2 *>(g + stw) = make_uint2(E1o[0], E1o[1]);
                         *reinterpret_cast<uint2 *>(g + 2 * stw) = make_uint2(E2o[0], E2o[1]);
@@ -515,7 +533,7 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
             if (width > 0) { rpos = dp_beg + (kr & 0xffff); lpos = dp_beg + (0xffff - (kl & 0xffff)); }
             prev_info = make_int4(B.beg_sn, B.end_sn, lpos, rpos);
             if (lane == 0) {
-                ring_info[i % RING] = prev_info;
+                ring_info[i & (RING - 1)] = prev_info;
                 rowinfo_p(A, S)[i] = prev_info;
                 rowtb_p(A, S)[i] = make_uint4(tbo, 2 * stw, (uint32_t)p0, (uint32_t)nbase);
             }
@@ -527,9 +545,18 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
         }
     }
     R.tbbytes = (unsigned long long)tb_used * 4;
+    RC.flush(R, qlen);
     __syncwarp();
     pick_best(A, S, N, qlen, R);
     return ST_OK;
 }
+
+#undef NEE
+#undef NOE1
+#undef NOE2
+#undef NE1
+#undef NE2
+#undef MATCH2
+#undef MISM2
 
 }  // namespace mpoa

@@ -222,6 +222,7 @@ static const void *variant_fn() { return reinterpret_cast<const void *>(&poa_gro
 static const void *kernel_of(int variant) {
     switch (variant) {
         case 2: return variant_fn<2>();
+        case 3: return variant_fn<3>();
         case 4: return variant_fn<4>();
         case 8: return variant_fn<8>();
         default: return variant_fn<0>();
@@ -235,6 +236,7 @@ size_t poa_smem_bytes(int variant, int wcap, int warps_per_block) {
     int words;
     switch (variant) {
         case 2: words = variant_warp_words<2>(wcap); break;
+        case 3: words = variant_warp_words<3>(wcap); break;
         case 4: words = variant_warp_words<4>(wcap); break;
         case 8: words = variant_warp_words<8>(wcap); break;
         default: words = variant_warp_words<0>(wcap); break;

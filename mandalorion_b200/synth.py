@@ -115,3 +115,37 @@ def make_groups(cfg, n_groups=None, first=0, random_strand=False, with_names=Fal
             reads.append((f"g{gi}_r{ri}", r.decode()) if with_names else r)
         groups.append(reads)
     return groups
+
+
+def _packed_chunk(args):
+    cfg, n, first = args
+    groups = make_groups(cfg, n, first=first)
+    counts = np.array([len(g) for g in groups], dtype=np.int64)
+    lens = np.array([len(r) for g in groups for r in g], dtype=np.int64)
+    blob = b"".join(r for g in groups for r in g)
+    return counts, lens, blob
+
+
+def make_packed(cfg, n_groups, first=0, workers=None, chunk=256):
+    """Packed arrays (group_read_off, read_base_off, bases) of groups [first, first+n_groups),
+    generated in parallel; identical to pack_groups(make_groups(...)) because every group has its
+    own RNG stream."""
+    import multiprocessing as mp
+    import os
+    if isinstance(cfg, str):
+        cfg = CONFIGS[cfg]
+    jobs = [(cfg, min(chunk, n_groups - s), first + s) for s in range(0, n_groups, chunk)]
+    workers = workers or min(len(jobs), os.cpu_count() or 1)
+    if workers <= 1 or len(jobs) == 1:
+        parts = [_packed_chunk(j) for j in jobs]
+    else:
+        with mp.get_context("fork").Pool(workers) as pool:
+            parts = pool.map(_packed_chunk, jobs)
+    counts = np.concatenate([p[0] for p in parts]) if parts else np.zeros(0, np.int64)
+    lens = np.concatenate([p[1] for p in parts]) if parts else np.zeros(0, np.int64)
+    gro = np.zeros(len(counts) + 1, dtype=np.int64)
+    gro[1:] = np.cumsum(counts)
+    rbo = np.zeros(len(lens) + 1, dtype=np.int64)
+    rbo[1:] = np.cumsum(lens)
+    bases = np.frombuffer(b"".join(p[2] for p in parts), dtype=np.uint8).copy()
+    return gro, rbo, bases

@@ -194,6 +194,7 @@ struct AlnOut {
     int best_score = 0;
     int bits = 0;
     int64_t band_cells = 0, int_ops = 0, full_cells = 0;
+    int max_width = 0;
     bool ok = false;
 };
 
@@ -297,6 +298,7 @@ void align_to_graph(Graph &g, const Par &P, const uint8_t *q, int qlen, DpScratc
         S.H.resize(off + width); S.E1.resize(off + width); S.E2.resize(off + width);
         S.F1.resize(off + width); S.F2.resize(off + width);
         R.band_cells += width;
+        if (width > R.max_width) R.max_width = width;
         R.int_ops += 17LL * width + 3LL * std::max(0, npre - 1) * width;
         R.full_cells += qlen + 1;
 
@@ -579,12 +581,14 @@ void run_group(const Par &P, int64_t r0, int64_t r1, const int64_t *read_base_of
         if (len <= 0) continue;  // abpoa_align_sequence_to_graph returns early, nothing is added
         if (!g.sorted && !topological_sort(g)) return;
         R.band_cells = R.int_ops = R.full_cells = 0;
+        R.max_width = 0;
         align_to_graph(g, P, seq.data(), len, S, R);
         out.st.n_alignments++;
         out.st.band_cells += R.band_cells;
         out.st.int_ops += R.int_ops;
         out.st.full_cells += R.full_cells;
         (R.bits == 16 ? out.st.n_align_i16 : out.st.n_align_i32)++;
+        if (R.max_width > out.st.reserved[0]) out.st.reserved[0] = R.max_width;  // widest band row (scheduling calibration)
         if (tr && tr->read_score) tr->read_score[r] = R.best_score;
         if (tr && tr->read_bits) tr->read_bits[r] = R.bits;
         if (tr && tr->read_band_cells) tr->read_band_cells[r] = R.band_cells;
@@ -600,6 +604,7 @@ void add_stats(mpoa_stats &a, const mpoa_stats &b) {
     a.n_groups += b.n_groups; a.n_reads += b.n_reads; a.n_alignments += b.n_alignments;
     a.band_cells += b.band_cells; a.full_cells += b.full_cells; a.int_ops += b.int_ops;
     a.n_align_i16 += b.n_align_i16; a.n_align_i32 += b.n_align_i32;
+    if (b.reserved[0] > a.reserved[0]) a.reserved[0] = b.reserved[0];
 }
 
 }  // namespace

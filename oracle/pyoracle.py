@@ -131,4 +131,5 @@ def oracle_consensus_batch(groups=None, packed=None, params=None, n_threads=1, t
     raw = cons_buf.tobytes()
     cons = [raw[cons_off[i]:cons_off[i + 1]] for i in range(ng)]
     stats = {k: getattr(st, k) for k, _ in _Stats._fields_ if k not in ("reserved", "phase_cycles")}
+    stats["max_band_width"] = int(st.reserved[0])
     return dict(cons=cons, status=status, stats=stats, trace=tr_arrays)

@@ -9,7 +9,8 @@ from mandalorion_b200.synth import make_groups  # noqa: E402
 cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-packed = pack_groups(make_groups(cfg, n))
+from mandalorion_b200.synth import make_packed
+packed = make_packed(cfg, n)
 ctx = PoaContext(0)
 ctx.upload(*packed)
 for _ in range(reps):
