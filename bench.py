@@ -32,10 +32,9 @@ UNIT = "groups/s"
 WORKLOAD = "cfg2: synthetic isoform groups, 10-50 reads, 0.5-4 kb log-uniform, 1% R2C2-like error"
 
 
-def make_batch(n_groups, first):
-    from mandalorion_b200 import pack_groups
-    from mandalorion_b200.synth import make_groups
-    return pack_groups(make_groups("cfg2", n_groups, first=first))
+def make_batch(n_groups, first, workers=None):
+    from mandalorion_b200.synth import make_packed
+    return make_packed("cfg2", n_groups, first=first, workers=workers)
 
 
 def algorithmic_bytes(stats, n_bases, cons_bases):
@@ -143,7 +142,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--groups", type=int, default=4096, help="cfg2 groups per GPU per step")
+    ap.add_argument("--groups", type=int, default=16384, help="cfg2 groups per GPU per step")
     ap.add_argument("--ref-groups", type=int, default=96, help="groups per step of the CPU reference arm")
     ap.add_argument("--cpu-sample", type=int, default=64, help="groups of the cpu_baseline sample")
     args = ap.parse_args()
@@ -173,7 +172,8 @@ def main():
         torch.cuda.synchronize()
 
     # every rank owns its own slice of the config (weak scaling); pinned host buffers for the e2e leg
-    gro, rbo, bases = make_batch(args.groups, first=rank * args.groups)
+    gro, rbo, bases = make_batch(args.groups, first=rank * args.groups,
+                                 workers=max(1, (os.cpu_count() or 1) // max(1, world)))
     pin = [torch.from_numpy(a).pin_memory() for a in (gro, rbo, bases)]
     gro_p, rbo_p, bases_p = [t.numpy() for t in pin]
     n_groups, n_bases = len(gro) - 1, int(rbo[-1])
@@ -247,13 +247,9 @@ def main():
                 traffic = json.load(open(prof)).get("dram_bytes_per_launch")
             except (OSError, ValueError):
                 traffic = None
-        int_peak = None
-        ip = os.path.join(ROOT, "profiles", "int_peak.json")
-        if os.path.exists(ip):
-            try:
-                int_peak = json.load(open(ip)).get("int_ops_per_sec")
-            except (OSError, ValueError):
-                int_peak = None
+        # INT-pipe peak measured live: VIADDMNMX.S16x2 warp-instructions/s x 32 lanes x 2 int16 ops
+        # (SURVEY.md 8d counts one s16x2 instruction as 2 ops)
+        int_peak = ctx.measure_int_peak() * 32 * 2
         int_achieved = stats["int_ops"] / (per_launch_ms * 1e-3)
         cores = os.cpu_count() or 1
         cpu_gps, cpu_gcups, cpu_dt = cpu_port_groups_per_sec(sample_of((gro, rbo, bases), args.cpu_sample), cores)
@@ -261,7 +257,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int32", "data": "synthetic",
+            "dtype": "int16x2 (int32 for reads > 6.5 kb)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "groups_per_gpu_per_step": n_groups, "reads": int(len(rbo) - 1),
                        "bases_per_gpu": n_bases, "parallelism": f"groups sharded over {world} GPU(s), no collective",
                        "cache": "inputs + per-step traceback/workspace traffic exceed the 126 MB L2"},
@@ -277,7 +273,8 @@ def main():
                          "note": "integer DP: the ALU/latency bound is int_roofline; HBM carries 1 B/cell"},
             "int_roofline": {"achieved_ops_per_s": int_achieved, "peak_ops_per_s": int_peak,
                              "frac": (int_achieved / int_peak) if int_peak else None,
-                             "ops_per_cell": 17, "unit": "int16-lane op/s"},
+                             "ops_per_cell": 17, "unit": "int16-lane op/s",
+                             "peak_source": "measured live: VIADDMNMX.S16x2 chains (mpoa_measure_int_peak) x 32 lanes x 2"},
             "phase_share": {k: v / max(1, stats["phase_cycles"]["busy"]) for k, v in stats["phase_cycles"].items()},
             "cpu_baseline": {"value": cpu_gps, "unit": UNIT, "cores": cores, "kind": "port", "gcups": cpu_gcups,
                              "sample": f"first {min(args.cpu_sample, n_groups)} groups of the same batch, oracle/ C++ scalar "

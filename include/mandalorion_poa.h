@@ -122,6 +122,10 @@ int  mpoa_set_stream(mpoa_ctx *ctx, void *cuda_stream);
 /* enable != 0: the next mpoa_batch_upload() also allocates the per-read trace arrays. */
 int  mpoa_set_trace(mpoa_ctx *ctx, int enable);
 
+/* INT-pipe roofline probe: measured rate (warp-wide instructions per second, whole GPU) of the
+ * DPX instruction the packed DP is built on (VIADDMNMX.S16x2). */
+int  mpoa_measure_int_peak(mpoa_ctx *ctx, double *warp_instr_per_sec);
+
 /*
  * Consensus of n_groups independent read groups, HOST buffers in, HOST buffers out.
  *   group_read_off[n_groups+1]  reads of group g are [group_read_off[g], group_read_off[g+1])

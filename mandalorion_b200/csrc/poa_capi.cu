@@ -23,6 +23,7 @@ cudaError_t launch_encode(const uint8_t *ascii, uint8_t *codes, int64_t n, cudaS
 cudaError_t launch_poa(int variant, const KernelArgs &A, int n_blocks, int warps_per_block, cudaStream_t stream);
 int poa_max_blocks_per_sm(int variant, int wcap, int warps_per_block);
 size_t poa_smem_bytes(int variant, int wcap, int warps_per_block);
+cudaError_t launch_int_peak(uint32_t *out, int blocks, int iters, cudaStream_t stream);
 cudaError_t launch_gather(const uint8_t *cons, const int64_t *region_off, const int64_t *out_off, uint8_t *out,
                           int64_t n_groups, cudaStream_t stream);
 }  // namespace mpoa
@@ -157,6 +158,31 @@ extern "C" int mpoa_set_stream(mpoa_ctx *ctx, void *cuda_stream) {
 extern "C" int mpoa_set_trace(mpoa_ctx *ctx, int enable) {
     if (!ctx) return MPOA_EINVAL;
     ctx->want_trace = enable ? 1 : 0;
+    return MPOA_OK;
+}
+
+/* Measured throughput of the DPX instruction the packed DP is built on (VIADDMNMX.S16x2), in
+ * warp-wide instructions per second over the whole GPU: the INT-pipe roofline denominator. */
+extern "C" int mpoa_measure_int_peak(mpoa_ctx *ctx, double *warp_instr_per_sec) {
+    if (!ctx || !warp_instr_per_sec) return MPOA_EINVAL;
+    CK(cudaSetDevice(ctx->dev));
+    const int blocks = ctx->n_sm * 8, iters = 20000;
+    uint32_t *d_out = nullptr;
+    CK(cudaMalloc(&d_out, (size_t)blocks * 256 * sizeof(uint32_t)));
+    CK(launch_int_peak(d_out, blocks, 1000, ctx->stream));   // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        CK(launch_int_peak(d_out, blocks, iters, ctx->stream));
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        const double instr = (double)blocks * 8 /* warps */ * 8 /* chains */ * (double)iters;
+        best = std::max(best, instr / (ms * 1e-3));
+    }
+    cudaFree(d_out);
+    *warp_instr_per_sec = best;
     return MPOA_OK;
 }
 

@@ -140,7 +140,8 @@ __host__ __device__ constexpr int variant_warp_words(int wcap) {
 }
 
 template <int V>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) poa_group_kernel(const __grid_constant__ KernelArgs A) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (V == 2 ? 6 : V == 3 ? 5 : V == 4 ? 4 : V == 8 ? 3 : 3))
+poa_group_kernel(const __grid_constant__ KernelArgs A) {
     extern __shared__ __align__(16) int smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per_warp = variant_warp_words<V>(A.wcap);
@@ -191,6 +192,28 @@ __global__ void gather_consensus_kernel(const uint8_t *__restrict__ cons, const 
         uint8_t *dst = out + out_off[g];
         for (int64_t k = lane; k < n; k += 32) dst[k] = src[k];
     }
+}
+
+/* INT-pipe roofline probe: register-resident chains of the DPX op the DP is built on
+ * (VIADDMNMX.S16x2), 8 independent chains per thread.  out[] only defeats dead-code removal. */
+__global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, uint32_t seed, int iters) {
+    uint32_t a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = seed + threadIdx.x * 8 + k;
+    const uint32_t c = seed | 0x00010001u, f = seed * 3u;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = __viaddmax_s16x2(a[k], c, f + k);
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r ^= a[k];
+    if (r == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+cudaError_t launch_int_peak(uint32_t *out, int blocks, int iters, cudaStream_t stream) {
+    int_peak_kernel<<<blocks, 256, 0, stream>>>(out, 12345u, iters);
+    return cudaGetLastError();
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -62,7 +62,7 @@ _lib = None
 
 # every symbol include/mandalorion_poa.h declares
 ABI_SYMBOLS = ("mpoa_abi_version", "mpoa_default_params", "mpoa_create", "mpoa_destroy", "mpoa_last_error",
-               "mpoa_set_stream", "mpoa_set_trace", "mpoa_consensus_batch", "mpoa_batch_upload", "mpoa_batch_run",
+               "mpoa_set_stream", "mpoa_set_trace", "mpoa_measure_int_peak", "mpoa_consensus_batch", "mpoa_batch_upload", "mpoa_batch_run",
                "mpoa_batch_fetch")
 
 
@@ -82,6 +82,7 @@ def _load():
         lib.mpoa_destroy.argtypes = [C.c_void_p]
         lib.mpoa_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         lib.mpoa_set_trace.argtypes = [C.c_void_p, C.c_int]
+        lib.mpoa_measure_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         lib.mpoa_batch_upload.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 4
         lib.mpoa_batch_run.argtypes = [C.c_void_p, C.c_void_p]
         lib.mpoa_batch_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
@@ -157,6 +158,12 @@ class PoaContext:
 
     def set_trace(self, enable):
         self._check(self._lib.mpoa_set_trace(self._h, int(bool(enable))), "mpoa_set_trace")
+
+    def measure_int_peak(self):
+        """Warp-wide VIADDMNMX.S16x2 instructions per second over the whole GPU (INT-pipe roofline)."""
+        v = C.c_double()
+        self._check(self._lib.mpoa_measure_int_peak(self._h, C.byref(v)), "mpoa_measure_int_peak")
+        return v.value
 
     @staticmethod
     def _stats_dict(st):
