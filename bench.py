@@ -142,7 +142,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--groups", type=int, default=16384, help="cfg2 groups per GPU per step")
+    ap.add_argument("--groups", type=int, default=32768, help="cfg2 groups per GPU per step")
     ap.add_argument("--ref-groups", type=int, default=1024, help="groups per step of the CPU reference arm")
     ap.add_argument("--cpu-sample", type=int, default=3072, help="groups of the cpu_baseline sample")
     args = ap.parse_args()

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -308,7 +309,7 @@ static SlotLayout make_layout(const Caps &c) {
  * band capacity in cells.  A group escalates along this list when its band or scores outgrow
  * the level it was scheduled at. */
 struct Level { int variant, wcap; };
-static const Level kLevels[] = {{2, 128}, {3, 192}, {4, 256}, {8, 512}, {0, 256}, {0, 512}, {0, 1024}, {0, 2048}, {0, 4096},
+static const Level kLevels[] = {{2, 128}, {4, 256}, {8, 512}, {0, 256}, {0, 512}, {0, 1024}, {0, 2048}, {0, 4096},
                                 {0, 8192}, {0, 16384}};
 static const int kNumLevels = (int)(sizeof(kLevels) / sizeof(kLevels[0]));
 
@@ -333,9 +334,10 @@ struct Launch {
     double cost = 0;
     uint64_t ws_off = 0;
     size_t q_off = 0;
+    bool covers[32] = {false};   // levels whose groups this launch may steal
 };
 
-static void fill_args(mpoa_ctx *ctx, const Launch &ln, int k, KernelArgs &A) {
+static void fill_args(mpoa_ctx *ctx, const Launch &ln, int k, KernelArgs &A) {  // steal queues: see run_round
     std::memset(&A, 0, sizeof(A));
     A.codes = ctx->d_codes; A.read_off = ctx->d_rbo; A.group_read_off = ctx->d_gro;
     A.queue = ctx->d_queue + ln.q_off; A.n_queue = (int)ln.gs.size(); A.queue_head = ctx->d_queue_head + k;
@@ -379,9 +381,13 @@ static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_la
             for (int32_t g : ln.gs) ctx->h_status[g] = ST_EMPTY;
             continue;
         }
+        if (const char *b = getenv("MPOA_BPS")) ln.bps = std::min(ln.bps, std::max(1, atoi(b)));   // tuning aid
         ln.L = make_layout(ln.c);
         ln.cost = 0;
         for (int32_t g : ln.gs) ln.cost += ctx->ginfo[g].cost;
+        /* per-row cost grows with the words per lane; wider levels are also over-provisioned on
+         * purpose: they finish first and then steal from the narrower ones */
+        ln.cost *= ln.c.variant == 0 ? 6.0 : (ln.c.variant == 2 ? 1.0 : ln.c.variant == 3 ? 1.6 : ln.c.variant == 4 ? 2.2 : 3.5);
         tot_cost += ln.cost;
         live.push_back(&ln);
     }
@@ -424,6 +430,8 @@ static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_la
     }
     CK(cudaMemcpyAsync(ctx->d_queue, hq.data(), hq.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_queue_head, 0, 16 * sizeof(int), ctx->stream));
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> vev;
+    std::vector<int> vidx;
     const bool fork = live.size() > 1;
     if (fork) {
         if (!ctx->fork_ev) CK(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
@@ -445,11 +453,39 @@ static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_la
         }
         KernelArgs A;
         fill_args(ctx, *ln, (int)k, A);
+        /* work stealing: once its own queue is empty a level drains the queues of the narrower
+         * levels it covers (widest first); its slot capacities were sized for them (see caller) */
+        A.n_steal = 0;
+        for (int o = (int)live.size() - 1; o >= 0 && A.n_steal < 4; --o) {
+            if (o == (int)k || live[o]->n_blocks <= 0) continue;
+            if (!ln->covers[live[o]->lv]) continue;
+            A.steal_queue[A.n_steal] = ctx->d_queue + live[o]->q_off;
+            A.steal_n[A.n_steal] = (int)live[o]->gs.size();
+            A.steal_head[A.n_steal] = ctx->d_queue_head + o;
+            ++A.n_steal;
+        }
+        cudaEvent_t v0 = nullptr, v1 = nullptr;
+        const bool verbose = getenv("MPOA_VERBOSE") != nullptr;
+        if (verbose) { cudaEventCreate(&v0); cudaEventCreate(&v1); cudaEventRecord(v0, st); }
         CK(launch_poa(ln->c.variant, A, (int)ln->n_blocks, ln->wpb, st));
+        if (verbose) { cudaEventRecord(v1, st); vev.push_back({v0, v1}); vidx.push_back((int)k); }
         ++*n_launch;
         if (fork) {
             CK(cudaEventRecord(ctx->join_ev[k], st));
             CK(cudaStreamWaitEvent(ctx->stream, ctx->join_ev[k], 0));
+        }
+    }
+    if (!vev.empty()) {
+        cudaStreamSynchronize(ctx->stream);
+        for (size_t q = 0; q < vev.size(); ++q) {
+            float ms = 0;
+            cudaEventSynchronize(vev[q].second);
+            cudaEventElapsedTime(&ms, vev[q].first, vev[q].second);
+            const Launch *ln = live[vidx[q]];
+            fprintf(stderr, "[mpoa] level V=%d wcap=%d groups=%zu blocks=%lld x %d warps (bps %d) slot=%.1f MB cost=%.3g: %.1f ms\n",
+                    ln->c.variant, ln->c.wcap, ln->gs.size(), (long long)ln->n_blocks, ln->wpb, ln->bps,
+                    ln->L.slot_bytes / 1e6, ln->cost, ms);
+            cudaEventDestroy(vev[q].first); cudaEventDestroy(vev[q].second);
         }
     }
     return MPOA_OK;
@@ -474,6 +510,10 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
     for (int64_t g = 0; g < ng; ++g) {
         GroupInfo &gi = ctx->ginfo[g];
         gi.level = (int8_t)first_level(gi.lanes16 != 0, ctx->params.debug_small_caps ? 1 : gi.wneed);
+        if (const char *ml = getenv("MPOA_MIN_LEVEL")) {   // tuning aid: schedule everything at >= this level
+            const int m = atoi(ml);
+            if (gi.lanes16 && gi.level < m && m < 3) gi.level = (int8_t)m;
+        }
         gi.attempt = 0;
     }
     int64_t n_launch = 0;
@@ -483,6 +523,10 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
          * wider level that covers it (launches of one batch are serialised) */
         std::vector<std::vector<int32_t>> bins(kNumLevels);
         for (int32_t g : pending) bins[ctx->ginfo[g].level].push_back(g);
+        /* rows cost almost the same in the 128- and 256-cell variants (fixed per-row work dominates)
+         * while a second concurrent launch splits the SMs and leaves stragglers: the narrow packed
+         * level is always run inside the 256-cell launch when there is one */
+        if (!bins[1].empty() && !bins[0].empty() && !getenv("MPOA_NO_FOLD")) { bins[1].insert(bins[1].end(), bins[0].begin(), bins[0].end()); bins[0].clear(); }
         const size_t min_groups = (size_t)ctx->n_sm;
         for (int a = 0; a < kNumLevels; ++a) {
             if (bins[a].empty() || bins[a].size() >= min_groups) continue;
@@ -534,6 +578,17 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
             launches.back().gs = gs;
             launches.back().c = c;
         }
+        /* a launch may steal the groups of every narrower level of the same lane family that runs
+         * in this round: give it capacities that cover them */
+        for (Launch &a : launches)
+            for (const Launch &b : launches) {
+                if (&a == &b) continue;
+                const bool fam = (a.c.variant == 0) == (b.c.variant == 0);
+                if (!fam || b.c.wcap >= a.c.wcap) continue;
+                a.covers[b.lv] = true;
+                a.c.ncap = std::max(a.c.ncap, b.c.ncap); a.c.ecap = std::max(a.c.ecap, b.c.ecap);
+                a.c.qcap = std::max(a.c.qcap, b.c.qcap); a.c.tbcap = std::max(a.c.tbcap, b.c.tbcap);
+            }
         {
             const int rc = run_round(ctx, launches, &n_launch);
             if (rc < 0) return rc;

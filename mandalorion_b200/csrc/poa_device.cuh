@@ -70,6 +70,11 @@ struct KernelArgs {
     const int32_t *queue;            // group indices to process, heaviest first
     int n_queue;
     int *queue_head;
+    /* queues of NARROWER levels running concurrently: drained once the own queue is empty */
+    int n_steal;
+    const int32_t *steal_queue[4];
+    int steal_n[4];
+    int *steal_head[4];
     uint8_t *ws;                     // n_slots * L.slot_bytes
     SlotLayout L;
     uint8_t *cons;                   // consensus bytes, region of group g at cons_off[g]

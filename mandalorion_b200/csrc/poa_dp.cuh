@@ -390,25 +390,60 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
             uint32_t M2[WPL], EA[WPL], EB[WPL];
 #pragma unroll
             for (int m = 0; m < WPL; ++m) { M2[m] = NEG2; EA[m] = NEG2; EB[m] = NEG2; }
-            auto gather = [&](const uint32_t *Hp, int st, int pw, int shw) {
+            /* One predecessor row.  A lane's WPL words map to pred words [wp0, wp0+WPL): when they
+             * are all inside the pred's band they are fetched with one vector load per array (no
+             * bank conflicts); the word left of them (diagonal of the lane's first cell) comes from
+             * the neighbouring lane by shuffle. */
+            auto gather = [&](const uint32_t *Hp, int st, int pw, int shw, bool aligned) {
                 const int wp0 = wl0 + shw;
-                uint32_t hl = ((unsigned)(wp0 - 1) < (unsigned)pw) ? Hp[wp0 - 1] : NEG2;
+                uint32_t hw[WPL], e1w[WPL], e2w[WPL];
+                const bool full = aligned && wp0 >= 0 && wp0 + WPL <= pw;
+                if (full) {
+                    if constexpr (WPL == 2) {
+                        const uint2 a = *reinterpret_cast<const uint2 *>(Hp + wp0);
+                        const uint2 b = *reinterpret_cast<const uint2 *>(Hp + st + wp0);
+                        const uint2 c = *reinterpret_cast<const uint2 *>(Hp + 2 * st + wp0);
+                        hw[0] = a.x; hw[1] = a.y; e1w[0] = b.x; e1w[1] = b.y; e2w[0] = c.x; e2w[1] = c.y;
+                    } else if constexpr (WPL % 4 == 0) {
+#pragma unroll
+                        for (int m = 0; m < WPL; m += 4) {
+                            const uint4 a = *reinterpret_cast<const uint4 *>(Hp + wp0 + m);
+                            const uint4 b = *reinterpret_cast<const uint4 *>(Hp + st + wp0 + m);
+                            const uint4 c = *reinterpret_cast<const uint4 *>(Hp + 2 * st + wp0 + m);
+                            hw[m] = a.x; hw[m + 1] = a.y; hw[m + 2] = a.z; hw[m + 3] = a.w;
+                            e1w[m] = b.x; e1w[m + 1] = b.y; e1w[m + 2] = b.z; e1w[m + 3] = b.w;
+                            e2w[m] = c.x; e2w[m + 1] = c.y; e2w[m + 2] = c.z; e2w[m + 3] = c.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < WPL; ++m) { hw[m] = Hp[wp0 + m]; e1w[m] = Hp[st + wp0 + m]; e2w[m] = Hp[2 * st + wp0 + m]; }
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < WPL; ++m) {
+                        const int wp = wp0 + m;
+                        const bool v = (unsigned)wp < (unsigned)pw;
+                        hw[m] = v ? Hp[wp] : NEG2; e1w[m] = v ? Hp[st + wp] : NEG2; e2w[m] = v ? Hp[2 * st + wp] : NEG2;
+                    }
+                }
+                /* word wp0-1: last word of the lane below, or a direct load at lane 0 */
+                uint32_t hl = __shfl_up_sync(FULL, hw[WPL - 1], 1);
+                if (lane == 0) hl = ((unsigned)(wp0 - 1) < (unsigned)pw) ? Hp[wp0 - 1] : NEG2;
+                if (wp0 <= 0) hl = NEG2;
 #pragma unroll
                 for (int m = 0; m < WPL; ++m) {
-                    const int wp = wp0 + m;
-                    const bool v = (unsigned)wp < (unsigned)pw;
-                    const uint32_t hw = v ? Hp[wp] : NEG2;
-                    const uint32_t e1w = v ? Hp[st + wp] : NEG2, e2w = v ? Hp[2 * st + wp] : NEG2;
-                    const uint32_t dg = v ? __byte_perm(hl, hw, 0x5432) : NEG2;
+                    const bool v = (unsigned)(wp0 + m) < (unsigned)pw;
+                    const uint32_t dg = v ? __byte_perm(hl, hw[m], 0x5432) : NEG2;
                     M2[m] = __vmaxs2(M2[m], dg);
-                    EA[m] = __vmaxs2(EA[m], e1w);
-                    EB[m] = __vmaxs2(EB[m], e2w);
-                    hl = hw;
+                    EA[m] = __vmaxs2(EA[m], e1w[m]);
+                    EB[m] = __vmaxs2(EB[m], e2w[m]);
+                    hl = hw[m];
                 }
             };
             if (simple) {
+                const int shw = (dp_beg - (prev_info.x << lg)) >> 1;
                 gather(ring + ((i - 1) & (RING - 1)) * 3 * RW + RING_PAD, RW,
-                       ((prev_info.y - prev_info.x + 1) << lg) >> 1, (dp_beg - (prev_info.x << lg)) >> 1);
+                       ((prev_info.y - prev_info.x + 1) << lg) >> 1, shw, (shw % WPL) == 0);
             } else {
                 for (int k = 0; k < npre; ++k) {
                     const int p = k == 0 ? p0 : (int)in_row[in0 + k];
@@ -416,11 +451,11 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                     const int4 pi = (p == i - 1) ? prev_info : (near ? ring_info[p & (RING - 1)] : rowinfo_p(A, S)[p]);
                     const int pw = ((pi.y - pi.x + 1) << lg) >> 1;             // words of the pred's rounded band
                     const int shw = (dp_beg - (pi.x << lg)) >> 1;              // our word 0 = pred word shw
-                    if (near) gather(ring + (p & (RING - 1)) * 3 * RW + RING_PAD, RW, pw, shw);
+                    if (near) gather(ring + (p & (RING - 1)) * 3 * RW + RING_PAD, RW, pw, shw, (shw % WPL) == 0);
                     else {
                         const uint4 rt = rowtb_p(A, S)[p];
                         const int pst = (int)(rt.y >> 1);
-                        gather(tb + rt.x, pst, min(pw, pst), shw);
+                        gather(tb + rt.x, pst, min(pw, pst), shw, false);
                     }
                 }
             }
@@ -537,9 +572,14 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                 rowinfo_p(A, S)[i] = prev_info;
                 rowtb_p(A, S)[i] = make_uint4(tbo, 2 * stw, (uint32_t)p0, (uint32_t)nbase);
             }
-            if ((meta & META_TOSINK) && (width == 0 ? lane == 0 : (width - 1) / CPL == lane)) {
-                const int t = (width - 1) % CPL;
-                rowbest_p(A, S)[i] = width > 0 ? ((t & 1) ? hi16(Hw[t >> 1]) : lo16(Hw[t >> 1])) : NEG;
+            if (meta & META_TOSINK) {
+                /* H at the last cell of the row: the global best is picked among these after the DP */
+                int last = NEG;
+                bool mine = width == 0 && lane == 0;
+#pragma unroll
+                for (int t = 0; t < CPL; ++t)
+                    if (col0 + t == width - 1) { last = (t & 1) ? hi16(Hw[t >> 1]) : lo16(Hw[t >> 1]); mine = true; }
+                if (mine) rowbest_p(A, S)[i] = last;
             }
             __syncwarp();
         }

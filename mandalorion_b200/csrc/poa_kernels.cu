@@ -140,7 +140,7 @@ __host__ __device__ constexpr int variant_warp_words(int wcap) {
 }
 
 template <int V>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (V == 2 ? 6 : V == 3 ? 5 : V == 4 ? 4 : V == 8 ? 3 : 3))
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (V == 2 ? 4 : V == 3 ? 4 : V == 4 ? 4 : V == 8 ? 3 : 3))
 poa_group_kernel(const __grid_constant__ KernelArgs A) {
     extern __shared__ __align__(16) int smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -151,12 +151,18 @@ poa_group_kernel(const __grid_constant__ KernelArgs A) {
     unsigned long long st[SI_COUNT];
 #pragma unroll
     for (int k = 0; k < SI_COUNT; ++k) st[k] = 0;
+    int src = -1;   // -1: own queue, k >= 0: steal queue k
     for (;;) {
-        int qi = 0;
-        if (lane == 0) qi = atomicAdd(A.queue_head, 1);
-        qi = __shfl_sync(FULL, qi, 0);
-        if (qi >= A.n_queue) break;
-        const int g = A.queue[qi];
+        int qi = 0, g = -1;
+        for (;;) {
+            int *head = src < 0 ? A.queue_head : A.steal_head[src];
+            const int n = src < 0 ? A.n_queue : A.steal_n[src];
+            if (lane == 0) qi = atomicAdd(head, 1);
+            qi = __shfl_sync(FULL, qi, 0);
+            if (qi < n) { g = (src < 0 ? A.queue : A.steal_queue[src])[qi]; break; }
+            if (++src >= A.n_steal) break;
+        }
+        if (g < 0) break;
         unsigned long long gst[SI_COUNT];
 #pragma unroll
         for (int k = 0; k < SI_COUNT; ++k) gst[k] = 0;
