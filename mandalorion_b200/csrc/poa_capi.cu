@@ -360,6 +360,7 @@ static void fill_args(mpoa_ctx *ctx, const Launch &ln, int k, KernelArgs &A) {  
     A.K.ne1 = p2(-A.P.e1, -A.P.e1); A.K.ne2 = p2(-A.P.e2, -A.P.e2);
     A.K.match2 = p2(A.P.match, A.P.match); A.K.mism2 = p2(-A.P.mismatch, -A.P.mismatch);
     for (int d = 0; d < 5; ++d) A.K.dec[d] = p2(-A.P.e1 * cpl * (1 << d), -A.P.e2 * cpl * (1 << d));
+    for (int t = 0; t < 16; ++t) A.K.tdec[t] = p2(-A.P.e1 * t, -A.P.e2 * t);
 }
 
 /*

@@ -49,6 +49,7 @@ struct Packed16 {
     uint32_t ne1, ne2;         // (-e1,-e1), (-e2,-e2)
     uint32_t match2, mism2;    // (match,match), (-mismatch,-mismatch)
     uint32_t dec[5];           // decay of the cross-lane F scan at distance 1,2,4,8,16 lanes
+    uint32_t tdec[16];         // t * (-e1,-e2): decay inside a lane at cell t
 };
 
 /* byte offsets of the arrays inside one warp's HBM workspace ("slot") */

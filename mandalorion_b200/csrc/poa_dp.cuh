@@ -249,11 +249,14 @@ __device__ __forceinline__ uint32_t pack2(int lo, int hi) { return ((uint32_t)lo
 __device__ __forceinline__ int lo16(uint32_t w) { return (int)(short)(w & 0xffffu); }
 __device__ __forceinline__ int hi16(uint32_t w) { return (int)w >> 16; }
 
-/* shared-memory words of one warp: RING rows x 3 arrays x (32*WPL + 2*RING_PAD) + ring_info */
+/* shared-memory words of one warp: RING rows x 3 arrays x (32*WPL + 2*RING_PAD), the query
+ * profile of the rows' current column window (5 bases x 32*WPL words) and ring_info */
 template <int WPL>
 __host__ __device__ constexpr int ring16_row_words() { return 32 * WPL + 2 * RING_PAD; }
 template <int WPL>
-__host__ __device__ constexpr int ring16_warp_words() { return RING * 3 * ring16_row_words<WPL>() + RING * 4; }
+__host__ __device__ constexpr int ring16_rows() { return WPL >= 4 ? 4 : 8; }   // rows kept in shared memory
+template <int WPL>
+__host__ __device__ constexpr int ring16_warp_words() { return ring16_rows<WPL>() * 3 * ring16_row_words<WPL>() + 5 * 32 * WPL + RING * 4; }
 
 template <int WPL>
 __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, int N, const uint8_t *__restrict__ q,
@@ -261,7 +264,10 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
     constexpr int CPL = 2 * WPL;              // cells per lane
     constexpr int WCAP = 32 * CPL;            // cells per row
     constexpr int RW = ring16_row_words<WPL>();
+    constexpr int PW = 32 * WPL;              // words of one profile row
+    constexpr int RINGV = ring16_rows<WPL>();
     const DevParams &P = A.P;
+    const Packed16 &K = A.K;
     const uint32_t *in_off = in_off_p(A, S), *in_row = in_row_p(A, S);
     uint32_t *tb = reinterpret_cast<uint32_t *>(tb_p(A, S));   // words = pairs of int16 cells
     const uint32_t tbcap = (uint32_t)min(A.L.tbcap / 4, (uint64_t)0xfffffff0u);
@@ -271,18 +277,14 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
     const int w = P.wb < 0 ? qlen : P.wb + (int)__fmul_rn(P.wf, (float)qlen);
     uint32_t tb_used = 0;                     // words
     RowCount RC = {0, 0, 0};
+    int err = ST_OK;                          // sticky: checked once per window of 32 rows
 
-    const Packed16 &K = A.K;
-    const uint32_t NEG2 = pack2(NEG16, NEG16);
-#define NEE K.nee
-#define NOE1 K.noe1
-#define NOE2 K.noe2
-#define NE1 K.ne1
-#define NE2 K.ne2
-#define MATCH2 K.match2
-#define MISM2 K.mism2
+    const uint32_t NEG2 = K.neg2;
     const int wl0 = lane * WPL;               // first word of this lane inside a row
     const int col0 = lane * CPL;              // first cell
+    uint32_t *prof = ring + RINGV * 3 * RW;    // [5][PW] match/mismatch words of the current window
+    /* vector accesses of a lane's WPL words need the pred row shifted by whole lanes */
+    const bool lanes_whole = ((R.pn >> 1) % WPL) == 0;
 
     /* row 0: the source */
     int4 prev_info;
@@ -309,6 +311,7 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
             const uint32_t e1w = c == 0 ? pack2(-P.oe1, NEG16) : NEG2, e2w = c == 0 ? pack2(-P.oe2, NEG16) : NEG2;
             Hs[wl0 + m] = hw; E1s[wl0 + m] = e1w; E2s[wl0 + m] = e2w;
             if ((uint32_t)(wl0 + m) < stw) { tb[wl0 + m] = hw; tb[stw + wl0 + m] = e1w; tb[2 * stw + wl0 + m] = e2w; }
+            prof[4 * PW + wl0 + m] = 0;       // a node base N scores 0 against everything
         }
         prev_info = make_int4(0, end_sn, 0, 0);
         if (lane == 0) {
@@ -320,41 +323,46 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
         __syncwarp();
     }
 
-    uint32_t qw[(CPL + 3) / 4], qn[WPL];      // query bases of this lane's cells, N masks per word
-    int q_for_beg = -1;
+    int prof_beg = -1;                        // band start the profile was built for
+    int4 *rowinfo_g = rowinfo_p(A, S);
+    uint4 *rowtb_g = rowtb_p(A, S);
 
     for (int w0 = 1; w0 < N - 1; w0 += 32) {
-        int m_meta = 0, m_in0 = 0, m_in1 = 0, m_rem = 0, m_p0 = 0;
+        /* row metadata of 32 rows at once: a = base | flags | npre<<5 | remain<<13 */
+        uint32_t m_a = 0;
+        int m_in0 = 0, m_p0 = 0;
         {
             const int r = w0 + lane;
             if (r < N - 1) {
-                m_meta = (int)meta_p(A, S)[r];
                 m_in0 = (int)in_off[r];
-                m_in1 = (int)in_off[r + 1];
-                m_rem = remain_p(A, S)[r];
-                m_p0 = m_in1 > m_in0 ? (int)in_row[m_in0] : 0;
+                const int npre = (int)in_off[r + 1] - m_in0;
+                m_a = (meta_p(A, S)[r] & 31u) | ((uint32_t)min(npre, 255) << 5) | ((uint32_t)remain_p(A, S)[r] << 13);
+                m_p0 = npre > 0 ? (int)in_row[m_in0] : 0;
             }
         }
         const int nrows = min(32, N - 1 - w0);
         for (int l = 0; l < nrows; ++l) {
             const int i = w0 + l;
-            const int meta = __shfl_sync(FULL, m_meta, l);
-            const int in0 = __shfl_sync(FULL, m_in0, l);
-            const int npre = __shfl_sync(FULL, m_in1, l) - in0;
-            const int rem = __shfl_sync(FULL, m_rem, l);
+            const uint32_t ma = __shfl_sync(FULL, m_a, l);
             const int p0 = __shfl_sync(FULL, m_p0, l);
-            const int nbase = meta & META_BASE;
+            const int nbase = ma & META_BASE;
+            const int rem = (int)(ma >> 13);
+            int npre = (ma >> 5) & 255;
+            int in0 = 0;
 
             /* most rows have ONE predecessor and it is the previous row: straight-line path */
             const bool simple = npre == 1 && p0 == i - 1;
-            int left = N, right = 0, minb = INT_MAX, maxe = -1;
+            int left, right, minb, maxe;
             if (simple) {
                 left = min(N, prev_info.z + 1); right = max(0, prev_info.w + 1);
                 minb = prev_info.x; maxe = prev_info.y;
             } else {
+                in0 = __shfl_sync(FULL, m_in0, l);
+                if (npre == 255) npre = (int)in_off[i + 1] - in0;
+                left = N; right = 0; minb = INT_MAX; maxe = -1;
                 for (int k = 0; k < npre; ++k) {
                     const int p = k == 0 ? p0 : (int)in_row[in0 + k];
-                    const int4 pi = (p == i - 1) ? prev_info : ((i - p < RING) ? ring_info[p & (RING - 1)] : rowinfo_p(A, S)[p]);
+                    const int4 pi = (p == i - 1) ? prev_info : ((i - p < RINGV) ? ring_info[p & (RINGV - 1)] : rowinfo_g[p]);
                     left = min(left, pi.z + 1);
                     right = max(right, pi.w + 1);
                     minb = min(minb, pi.x);
@@ -362,61 +370,65 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                 }
             }
             const Band B = make_band(left, right, minb, maxe, rem, qlen, w, lg);
-            const int width = B.width, dp_beg = B.dp_beg;
-            if (width > WCAP) return ST_RETRY_WIDE;
+            int width = B.width;
+            const int dp_beg = B.dp_beg;
+            if (width > WCAP) { err = ST_RETRY_WIDE; width = 0; }
             const uint32_t stw = (uint32_t)(((width + 1) >> 1) + WPL - 1) / WPL * WPL;
-            const uint32_t tbo = tb_used;
-            if (tbcap - tb_used < 3 * stw) return ST_RETRY;
-            tb_used += 3 * stw;
+            uint32_t tbo = tb_used;
+            const bool ovf = tbcap - tb_used < 3 * stw;
+            if (ovf) { if (err == ST_OK) err = ST_RETRY; tbo = 0; }
+            else tb_used += 3 * stw;
             RC.add(width, npre);
 
-            /* query bases under this lane's cells: q[j-1], j = dp_beg + col0 + t; reloaded only
-             * when the band start moves (every ~pn rows) */
-            if (dp_beg != q_for_beg) {
-                q_for_beg = dp_beg;
+            /* query profile of the window [dp_beg, dp_beg + WCAP): rebuilt only when the band start
+             * moves (every ~pn rows); prof[b][word] = (s(b, q[j-1]), s(b, q[j])) for the word's cells */
+            if (dp_beg != prof_beg) {
+                prof_beg = dp_beg;
+                __syncwarp();
 #pragma unroll
-                for (int m = 0; m < WPL; ++m) qn[m] = 0;
+                for (int m = 0; m < WPL; ++m) {
+                    const int j0 = dp_beg + col0 + 2 * m;     // the word's first cell; it consumes q[j0-1]
+                    const int qa = q[min(max(j0 - 1, 0), qlen - 1)], qb = q[min(max(j0, 0), qlen - 1)];
 #pragma unroll
-                for (int t = 0; t < CPL; ++t) {
-                    const int qi = min(max(dp_beg + col0 + t - 1, 0), qlen - 1);
-                    const uint32_t b = q[qi];
-                    if ((t & 3) == 0) qw[t >> 2] = 0;
-                    qw[t >> 2] |= b << (8 * (t & 3));
-                    if (b >= 4) qn[t >> 1] |= 0xffffu << (16 * (t & 1));
+                    for (int b = 0; b < 4; ++b) {
+                        const int sa = qa >= 4 ? 0 : (qa == b ? P.match : -P.mismatch);
+                        const int sb = qb >= 4 ? 0 : (qb == b ? P.match : -P.mismatch);
+                        prof[b * PW + wl0 + m] = pack2(sa, sb);
+                    }
                 }
+                __syncwarp();
             }
 
-            /* gather the diagonal and the deletion inputs from the predecessors */
+            /* gather the diagonal and the deletion inputs from the predecessors.  A lane's WPL
+             * words map to pred words [wp0, wp0+WPL); with the pred row shifted by whole lanes they
+             * are all inside the pred's band or all outside: one vector load per array (no bank
+             * conflicts), the word left of them comes from the neighbouring lane by shuffle. */
             uint32_t M2[WPL], EA[WPL], EB[WPL];
-#pragma unroll
-            for (int m = 0; m < WPL; ++m) { M2[m] = NEG2; EA[m] = NEG2; EB[m] = NEG2; }
-            /* One predecessor row.  A lane's WPL words map to pred words [wp0, wp0+WPL): when they
-             * are all inside the pred's band they are fetched with one vector load per array (no
-             * bank conflicts); the word left of them (diagonal of the lane's first cell) comes from
-             * the neighbouring lane by shuffle. */
-            auto gather = [&](const uint32_t *Hp, int st, int pw, int shw, bool aligned) {
+            auto gather = [&](const uint32_t *Hp, int st, int pw, int shw, bool vec, bool first) {
                 const int wp0 = wl0 + shw;
                 uint32_t hw[WPL], e1w[WPL], e2w[WPL];
-                const bool full = aligned && wp0 >= 0 && wp0 + WPL <= pw;
-                if (full) {
+                if (vec) {
+                    const bool in = wp0 >= 0 && wp0 + WPL <= pw;
+                    const uint32_t *src = Hp + (in ? wp0 : 0);
                     if constexpr (WPL == 2) {
-                        const uint2 a = *reinterpret_cast<const uint2 *>(Hp + wp0);
-                        const uint2 b = *reinterpret_cast<const uint2 *>(Hp + st + wp0);
-                        const uint2 c = *reinterpret_cast<const uint2 *>(Hp + 2 * st + wp0);
+                        const uint2 a = *reinterpret_cast<const uint2 *>(src);
+                        const uint2 b = *reinterpret_cast<const uint2 *>(src + st);
+                        const uint2 c = *reinterpret_cast<const uint2 *>(src + 2 * st);
                         hw[0] = a.x; hw[1] = a.y; e1w[0] = b.x; e1w[1] = b.y; e2w[0] = c.x; e2w[1] = c.y;
-                    } else if constexpr (WPL % 4 == 0) {
+                    } else {
 #pragma unroll
                         for (int m = 0; m < WPL; m += 4) {
-                            const uint4 a = *reinterpret_cast<const uint4 *>(Hp + wp0 + m);
-                            const uint4 b = *reinterpret_cast<const uint4 *>(Hp + st + wp0 + m);
-                            const uint4 c = *reinterpret_cast<const uint4 *>(Hp + 2 * st + wp0 + m);
+                            const uint4 a = *reinterpret_cast<const uint4 *>(src + m);
+                            const uint4 b = *reinterpret_cast<const uint4 *>(src + st + m);
+                            const uint4 c = *reinterpret_cast<const uint4 *>(src + 2 * st + m);
                             hw[m] = a.x; hw[m + 1] = a.y; hw[m + 2] = a.z; hw[m + 3] = a.w;
                             e1w[m] = b.x; e1w[m + 1] = b.y; e1w[m + 2] = b.z; e1w[m + 3] = b.w;
                             e2w[m] = c.x; e2w[m + 1] = c.y; e2w[m + 2] = c.z; e2w[m + 3] = c.w;
                         }
-                    } else {
+                    }
+                    if (!in) {
 #pragma unroll
-                        for (int m = 0; m < WPL; ++m) { hw[m] = Hp[wp0 + m]; e1w[m] = Hp[st + wp0 + m]; e2w[m] = Hp[2 * st + wp0 + m]; }
+                        for (int m = 0; m < WPL; ++m) { hw[m] = NEG2; e1w[m] = NEG2; e2w[m] = NEG2; }
                     }
                 } else {
 #pragma unroll
@@ -432,48 +444,52 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                 if (wp0 <= 0) hl = NEG2;
 #pragma unroll
                 for (int m = 0; m < WPL; ++m) {
+                    /* an out-of-band word holds NEG2 in hw/e1w/e2w already; its diagonal must be NEG2 too */
                     const bool v = (unsigned)(wp0 + m) < (unsigned)pw;
                     const uint32_t dg = v ? __byte_perm(hl, hw[m], 0x5432) : NEG2;
-                    M2[m] = __vmaxs2(M2[m], dg);
-                    EA[m] = __vmaxs2(EA[m], e1w[m]);
-                    EB[m] = __vmaxs2(EB[m], e2w[m]);
+                    if (first) { M2[m] = dg; EA[m] = e1w[m]; EB[m] = e2w[m]; }
+                    else { M2[m] = __vmaxs2(M2[m], dg); EA[m] = __vmaxs2(EA[m], e1w[m]); EB[m] = __vmaxs2(EB[m], e2w[m]); }
                     hl = hw[m];
                 }
             };
             if (simple) {
                 const int shw = (dp_beg - (prev_info.x << lg)) >> 1;
-                gather(ring + ((i - 1) & (RING - 1)) * 3 * RW + RING_PAD, RW,
-                       ((prev_info.y - prev_info.x + 1) << lg) >> 1, shw, (shw % WPL) == 0);
+                gather(ring + ((i - 1) & (RINGV - 1)) * 3 * RW + RING_PAD, RW,
+                       ((prev_info.y - prev_info.x + 1) << lg) >> 1, shw, lanes_whole, true);
             } else {
+#pragma unroll
+                for (int m = 0; m < WPL; ++m) { M2[m] = NEG2; EA[m] = NEG2; EB[m] = NEG2; }
                 for (int k = 0; k < npre; ++k) {
                     const int p = k == 0 ? p0 : (int)in_row[in0 + k];
-                    const bool near = i - p < RING;
-                    const int4 pi = (p == i - 1) ? prev_info : (near ? ring_info[p & (RING - 1)] : rowinfo_p(A, S)[p]);
+                    const bool near = i - p < RINGV;
+                    const int4 pi = (p == i - 1) ? prev_info : (near ? ring_info[p & (RINGV - 1)] : rowinfo_g[p]);
                     const int pw = ((pi.y - pi.x + 1) << lg) >> 1;             // words of the pred's rounded band
                     const int shw = (dp_beg - (pi.x << lg)) >> 1;              // our word 0 = pred word shw
-                    if (near) gather(ring + (p & (RING - 1)) * 3 * RW + RING_PAD, RW, pw, shw, (shw % WPL) == 0);
+                    if (near) gather(ring + (p & (RINGV - 1)) * 3 * RW + RING_PAD, RW, pw, shw, lanes_whole, false);
                     else {
-                        const uint4 rt = rowtb_p(A, S)[p];
+                        const uint4 rt = rowtb_g[p];
                         const int pst = (int)(rt.y >> 1);
-                        gather(tb + rt.x, pst, min(pw, pst), shw, false);
+                        gather(tb + rt.x, pst, min(pw, pst), shw, false, false);
                     }
                 }
             }
             /* first cell of the row's band: no diagonal at all */
             if (lane == 0) M2[0] = (M2[0] & 0xffff0000u) | (NEG2 & 0xffffu);
 
-            /* match/mismatch scores of this row's base against the lane's query bases */
+            /* match/mismatch scores from the profile row of this node's base */
             uint32_t S2[WPL];
-            if (nbase >= 4) {
+            {
+                const uint32_t *pr = prof + nbase * PW + wl0;
+                if constexpr (WPL == 2) { const uint2 a = *reinterpret_cast<const uint2 *>(pr); S2[0] = a.x; S2[1] = a.y; }
+                else if constexpr (WPL % 4 == 0) {
 #pragma unroll
-                for (int m = 0; m < WPL; ++m) S2[m] = 0;
-            } else {
-                const uint32_t nb4 = (uint32_t)nbase * 0x01010101u;
+                    for (int m = 0; m < WPL; m += 4) {
+                        const uint4 a = *reinterpret_cast<const uint4 *>(pr + m);
+                        S2[m] = a.x; S2[m + 1] = a.y; S2[m + 2] = a.z; S2[m + 3] = a.w;
+                    }
+                } else {
 #pragma unroll
-                for (int m = 0; m < WPL; ++m) {
-                    const uint32_t eq4 = __vcmpeq4(qw[m >> 1], nb4);
-                    const uint32_t mk = __byte_perm(eq4, eq4, (m & 1) ? 0x3322 : 0x1100);
-                    S2[m] = ((mk & MATCH2) | (~mk & MISM2)) & ~qn[m];
+                    for (int m = 0; m < WPL; ++m) S2[m] = pr[m];
                 }
             }
 
@@ -486,14 +502,14 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
             uint32_t X[CPL], FL[CPL];
 #pragma unroll
             for (int m = 0; m < WPL; ++m) {
-                const uint32_t a1 = __viaddmax_s16x2(HH[m], NOE1, NEG2), a2 = __viaddmax_s16x2(HH[m], NOE2, NEG2);
+                const uint32_t a1 = __viaddmax_s16x2(HH[m], K.noe1, NEG2), a2 = __viaddmax_s16x2(HH[m], K.noe2, NEG2);
                 X[2 * m] = __byte_perm(a1, a2, 0x5410);
                 X[2 * m + 1] = __byte_perm(a1, a2, 0x7632);
             }
             FL[0] = NEG2;
 #pragma unroll
-            for (int t = 1; t < CPL; ++t) FL[t] = __viaddmax_s16x2(FL[t - 1], NEE, X[t - 1]);
-            uint32_t T = __viaddmax_s16x2(FL[CPL - 1], NEE, X[CPL - 1]);
+            for (int t = 1; t < CPL; ++t) FL[t] = __viaddmax_s16x2(FL[t - 1], K.nee, X[t - 1]);
+            uint32_t T = __viaddmax_s16x2(FL[CPL - 1], K.nee, X[CPL - 1]);
 #pragma unroll
             for (int dd = 0; dd < 5; ++dd) {
                 const uint32_t up = __shfl_up_sync(FULL, T, 1 << dd);
@@ -503,11 +519,10 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
             if (lane == 0) C = NEG2;
             uint32_t F1w[WPL], F2w[WPL];
             {
-                uint32_t dec = 0, fa = 0;
+                uint32_t fa = 0;
 #pragma unroll
                 for (int t = 0; t < CPL; ++t) {
-                    const uint32_t ff = __viaddmax_s16x2(C, dec, FL[t]);
-                    dec = __vadd2(dec, NEE);
+                    const uint32_t ff = __viaddmax_s16x2(C, K.tdec[t], FL[t]);
                     if (t & 1) {
                         F1w[t >> 1] = __byte_perm(fa, ff, 0x5410);
                         F2w[t >> 1] = __byte_perm(fa, ff, 0x7632);
@@ -519,34 +534,44 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
 #pragma unroll
             for (int m = 0; m < WPL; ++m) {
                 Hw[m] = __vimax3_s16x2(HH[m], F1w[m], F2w[m]);
-                E1o[m] = __viaddmax_s16x2(EA[m], NE1, __viaddmax_s16x2(Hw[m], NOE1, NEG2));
-                E2o[m] = __viaddmax_s16x2(EB[m], NE2, __viaddmax_s16x2(Hw[m], NOE2, NEG2));
+                E1o[m] = __viaddmax_s16x2(EA[m], K.ne1, __viaddmax_s16x2(Hw[m], K.noe1, NEG2));
+                E2o[m] = __viaddmax_s16x2(EB[m], K.ne2, __viaddmax_s16x2(Hw[m], K.noe2, NEG2));
             }
 
             /* ring + HBM stores */
             {
-                uint32_t *Hr = ring + (i & (RING - 1)) * 3 * RW + RING_PAD;
-                const bool st = (uint32_t)wl0 < stw;
-#pragma unroll
-                for (int m = 0; m < WPL; ++m) {
-                    Hr[wl0 + m] = Hw[m]; Hr[RW + wl0 + m] = E1o[m]; Hr[2 * RW + wl0 + m] = E2o[m];
-                }
-                if (st) {
-                    uint32_t *g = tb + tbo + wl0;
-                    if constexpr (WPL == 3) {
-#pragma unroll
-                        for (int m = 0; m < WPL; ++m) { g[m] = Hw[m]; g[stw + m] = E1o[m]; g[2 * stw + m] = E2o[m]; }
-                    } else if constexpr (WPL == 2) {
+                uint32_t *Hr = ring + (i & (RINGV - 1)) * 3 * RW + RING_PAD + wl0;
+                uint32_t *g = tb + tbo + wl0;
+                const bool st = !ovf && (uint32_t)wl0 < stw;
+                if constexpr (WPL == 2) {
+                    *reinterpret_cast<uint2 *>(Hr) = make_uint2(Hw[0], Hw[1]);
+                    *reinterpret_cast<uint2 *>(Hr + RW) = make_uint2(E1o[0], E1o[1]);
+                    *reinterpret_cast<uint2 *>(Hr + 2 * RW) = make_uint2(E2o[0], E2o[1]);
+                    if (st) {
                         *reinterpret_cast<uint2 *>(g) = make_uint2(Hw[0], Hw[1]);
                         *reinterpret_cast<uint2 *>(g + stw) = make_uint2(E1o[0], E1o[1]);
                         *reinterpret_cast<uint2 *>(g + 2 * stw) = make_uint2(E2o[0], E2o[1]);
-                    } else {
+                    }
+                } else if constexpr (WPL % 4 == 0) {
 #pragma unroll
-                        for (int m = 0; m < WPL; m += 4) {
-                            *reinterpret_cast<uint4 *>(g + m) = make_uint4(Hw[m], Hw[m + 1], Hw[m + 2], Hw[m + 3]);
-                            *reinterpret_cast<uint4 *>(g + stw + m) = make_uint4(E1o[m], E1o[m + 1], E1o[m + 2], E1o[m + 3]);
-                            *reinterpret_cast<uint4 *>(g + 2 * stw + m) = make_uint4(E2o[m], E2o[m + 1], E2o[m + 2], E2o[m + 3]);
+                    for (int m = 0; m < WPL; m += 4) {
+                        const uint4 h4 = make_uint4(Hw[m], Hw[m + 1], Hw[m + 2], Hw[m + 3]);
+                        const uint4 a4 = make_uint4(E1o[m], E1o[m + 1], E1o[m + 2], E1o[m + 3]);
+                        const uint4 b4 = make_uint4(E2o[m], E2o[m + 1], E2o[m + 2], E2o[m + 3]);
+                        *reinterpret_cast<uint4 *>(Hr + m) = h4;
+                        *reinterpret_cast<uint4 *>(Hr + RW + m) = a4;
+                        *reinterpret_cast<uint4 *>(Hr + 2 * RW + m) = b4;
+                        if (st) {
+                            *reinterpret_cast<uint4 *>(g + m) = h4;
+                            *reinterpret_cast<uint4 *>(g + stw + m) = a4;
+                            *reinterpret_cast<uint4 *>(g + 2 * stw + m) = b4;
                         }
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < WPL; ++m) {
+                        Hr[m] = Hw[m]; Hr[RW + m] = E1o[m]; Hr[2 * RW + m] = E2o[m];
+                        if (st) { g[m] = Hw[m]; g[stw + m] = E1o[m]; g[2 * stw + m] = E2o[m]; }
                     }
                 }
             }
@@ -556,10 +581,10 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
 #pragma unroll
             for (int t = 0; t < CPL; ++t) {
                 const int c = col0 + t;
-                const int hv = (t & 1) ? hi16(Hw[t >> 1]) : lo16(Hw[t >> 1]);
+                const int hv = (t & 1) ? (int)(Hw[t >> 1] & 0xffff0000u) : (int)(Hw[t >> 1] << 16);
                 if (c < width) {
-                    kr = max(kr, (hv << 16) | c);
-                    kl = max(kl, (hv << 16) | (0xffff - c));
+                    kr = max(kr, hv | c);
+                    kl = max(kl, hv | (0xffff - c));
                 }
             }
             kr = __reduce_max_sync(FULL, kr);
@@ -568,11 +593,11 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
             if (width > 0) { rpos = dp_beg + (kr & 0xffff); lpos = dp_beg + (0xffff - (kl & 0xffff)); }
             prev_info = make_int4(B.beg_sn, B.end_sn, lpos, rpos);
             if (lane == 0) {
-                ring_info[i & (RING - 1)] = prev_info;
-                rowinfo_p(A, S)[i] = prev_info;
-                rowtb_p(A, S)[i] = make_uint4(tbo, 2 * stw, (uint32_t)p0, (uint32_t)nbase);
+                ring_info[i & (RINGV - 1)] = prev_info;
+                rowinfo_g[i] = prev_info;
+                rowtb_g[i] = make_uint4(tbo, 2 * stw, (uint32_t)p0, (uint32_t)nbase);
             }
-            if (meta & META_TOSINK) {
+            if (ma & META_TOSINK) {
                 /* H at the last cell of the row: the global best is picked among these after the DP */
                 int last = NEG;
                 bool mine = width == 0 && lane == 0;
@@ -583,6 +608,7 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
             }
             __syncwarp();
         }
+        if (err != ST_OK) return err;
     }
     R.tbbytes = (unsigned long long)tb_used * 4;
     RC.flush(R, qlen);
@@ -591,12 +617,5 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
     return ST_OK;
 }
 
-#undef NEE
-#undef NOE1
-#undef NOE2
-#undef NE1
-#undef NE2
-#undef MATCH2
-#undef MISM2
 
 }  // namespace mpoa

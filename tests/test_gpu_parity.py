@@ -128,17 +128,18 @@ def test_golden_vectors(built):
 
 
 def test_retry_paths_give_the_same_answer(built):
-    # debug_small_caps schedules the first attempt with a workspace sized for the first read only
-    # and the narrowest kernel variant: groups overflow (node capacity / band width / int16 lanes)
-    # and are re-run ON THE GPU with larger capacities or a wider variant -- never on the CPU
-    groups = make_groups("cfg1", 12) + make_groups("cfg3", 1) + make_groups("cfg4", 1)
-    packed = pack_groups(groups)
-    want = oracle_consensus_batch(packed=packed, trace=True, n_threads=os.cpu_count() or 1)
-    with PoaContext(0, PoaParams(debug_small_caps=1)) as ctx:
-        got = ctx.consensus_batch(packed=packed, trace=True)
-    assert_same(got, want, packed)
-    assert got["stats"]["n_retry_groups"] >= len(groups) - 1
-    assert got["stats"]["n_kernel_launches"] >= 2
+    # debug_small_caps schedules the first attempt with a workspace sized for the longest first read
+    # only and the narrowest kernel variant: groups overflow (node capacity / band width / int16
+    # lanes) and are re-run ON THE GPU with larger capacities or a wider variant -- never on the CPU
+    for groups, min_retry in ((make_groups("cfg1", 24), 4),
+                              (make_groups("cfg1", 6) + make_groups("cfg3", 1) + make_groups("cfg4", 1), 1)):
+        packed = pack_groups(groups)
+        want = oracle_consensus_batch(packed=packed, trace=True, n_threads=os.cpu_count() or 1)
+        with PoaContext(0, PoaParams(debug_small_caps=1)) as ctx:
+            got = ctx.consensus_batch(packed=packed, trace=True)
+        assert_same(got, want, packed)
+        assert got["stats"]["n_retry_groups"] >= min_retry
+        assert got["stats"]["n_kernel_launches"] >= 2
 
 
 def test_properties_at_scale(gpu_ctx):
