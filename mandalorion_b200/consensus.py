@@ -221,6 +221,20 @@ def consensus_for_loci(loci_seqdicts, ctx=None, orienter_factory=default_oriente
     return {root: {isoform: [pg.consensus, pg.names] for isoform, pg in iso.items()} for root, iso in results.items()}
 
 
+def finish_prepared(prepared, ctx=None):
+    """prepared: {root: {isoform: PendingGroup}} collected from the per-locus workers, which called
+    prepare_group() exactly where the reference calls determine_consensus() (defineIsoforms.py:89)
+    -- so the NumPy RNG stream of every worker is consumed like in the reference.  Runs ONE GPU
+    batch in the parent (after pool.join(); CUDA must not be initialised before the fork) and
+    returns {root: IsoData} with IsoData[isoform] = [consensus, names]."""
+    batcher = ConsensusBatcher(ctx)
+    for root in prepared:
+        for isoform in prepared[root]:
+            batcher.add(prepared[root][isoform])
+    batcher.flush()
+    return {root: {isoform: [pg.consensus, pg.names] for isoform, pg in iso.items()} for root, iso in prepared.items()}
+
+
 def write_isoform_files(roots, results, out_path):
     """Writer of Isoform_Consensi.fasta and reads2isoforms.txt, byte-compatible with the
     reference (defineIsoforms.py:155-166): global 1-based counter over loci in `roots` order,

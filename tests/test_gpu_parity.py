@@ -178,6 +178,29 @@ def test_three_stage_interface_reuses_resident_inputs(gpu_ctx):
     assert s1["kernel_ms"] > 0 and s1["tb_bytes"] >= s1["band_cells"]
 
 
+def test_dstep_files_match_the_reference_run(gpu_ctx, tmp_path):
+    """Module-D file parity on the GPU.  tests/golden/dstep/ was frozen in the build container by
+    tests/test_dstep_reference.py: the UNMODIFIED reference (its own main, fork pool, process_locus,
+    determine_consensus, writer) on synthetic tmp_SS/*.psl, with mappy stubbed and abpoa = oracle.
+    Here the prepared groups (subsample order + orientation, as computed inside the reference's
+    workers) go through the CUDA library in ONE batch and the two output files must be
+    byte-identical to what the reference wrote."""
+    from mandalorion_b200 import consensus as b200
+    gold = os.path.join(HERE, "golden", "dstep")
+    frozen = json.load(open(os.path.join(gold, "prepared.json")))
+    prepared = {}
+    for g in frozen["groups"]:
+        pg = b200.PendingGroup(names=g["names"], sequences=g["sequences"], seq_lengths=[], bypass=g["bypass"],
+                               seed=g["seed_flag"])
+        if pg.bypass:
+            pg.consensus = pg.sequences[0]
+        prepared.setdefault(g["root"], {})[g["isoform"]] = pg
+    results = b200.finish_prepared(prepared, ctx=gpu_ctx)
+    b200.write_isoform_files(frozen["roots"], results, str(tmp_path))
+    for name in ("Isoform_Consensi.fasta", "reads2isoforms.txt"):
+        assert open(os.path.join(tmp_path, name), "rb").read() == open(os.path.join(gold, name), "rb").read(), name
+
+
 def test_graft_smoke(built):
     import __graft_entry__ as ge
     ge.smoke()
