@@ -171,50 +171,68 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
     const uint32_t *out_off = out_off_p(A, S), *out_row = out_row_p(A, S), *in_off = in_off_p(A, S), *in_row = in_row_p(A, S);
     int32_t *out_w = out_w_p(A, S);
 
-    for (int r = lane; r < N; r += 32) { cnt_p(A, S)[r] = 0; addin_p(A, S)[r] = -1; addout_p(A, S)[r] = -1; grow_p(A, S)[r] = 0; }
+    /* Every pass below handles MK*32 elements per iteration in two stages: first all the
+     * (independent) dependent-load chains of the MK sub-chunks, then the cross-lane scans and the
+     * stores -- so MK global-memory round trips overlap instead of being paid one after another. */
+    constexpr int MK = 4;
+    int32_t *cnt = cnt_p(A, S), *addin = addin_p(A, S), *addout = addout_p(A, S), *srcof = srcof_p(A, S);
+    int32_t *pv = pv_p(A, S), *pkey = pkey_p(A, S), *pnew = pnew_p(A, S), *psib = psib_p(A, S);
+    int32_t *nin = nin_p(A, S), *nout = nout_p(A, S);
+    const int32_t *qmap = qmap_p(A, S), *creator = creator_p(A, S);
+    uint8_t *grow = grow_p(A, S);
+
+    for (int r = lane; r < N; r += 32) { cnt[r] = 0; addin[r] = -1; addout[r] = -1; grow[r] = 0; }
     __syncwarp();
 
     /* U1: resolve every query base to an existing row or a new node; order keys */
     int carry_key = 0, carry_new = 0;
-    for (int t0 = 0; t0 < qlen; t0 += 32) {
-        const int t = t0 + lane;
-        int isnew = 0, v = -1, key = -1, sibof = -1;
-        if (t < qlen) {
-            const int r = qmap_p(A, S)[t];
-            const int b = q[t];
-            if (r >= 0) {
-                if (base[r] == b) v = r;
-                else {
-                    const int sb = sib[r], before = sb >> 4, after = sb & 15;
-                    for (int x = r - before; x <= r + after; ++x)
-                        if (x != r && base[x] == b) v = x;
-                    if (v < 0) { isnew = 1; sibof = r; key = r + after; }
+    for (int t0 = 0; t0 < qlen; t0 += 32 * MK) {
+        int isnew[MK], v[MK], key[MK], sibof[MK];
+#pragma unroll
+        for (int u = 0; u < MK; ++u) {
+            const int t = t0 + u * 32 + lane;
+            isnew[u] = 0; v[u] = -1; key[u] = -1; sibof[u] = -1;
+            if (t < qlen) {
+                const int r = qmap[t];
+                const int b = q[t];
+                if (r >= 0) {
+                    if (base[r] == b) v[u] = r;
+                    else {
+                        const int sb = sib[r], before = sb >> 4, after = sb & 15;
+                        for (int x = r - before; x <= r + after; ++x)
+                            if (x != r && base[x] == b) v[u] = x;
+                        if (v[u] < 0) { isnew[u] = 1; sibof[u] = r; key[u] = r + after; }
+                    }
+                    if (!isnew[u]) key[u] = v[u] + (sib[v[u]] & 15);
+                    if (tr_aln) tr_aln[t] = creator[r];
+                } else {
+                    isnew[u] = 1;
+                    if (tr_aln) tr_aln[t] = -1;
                 }
-                if (!isnew) key = v + (sib[v] & 15);
-                if (tr_aln) tr_aln[t] = creator_p(A, S)[r];
-            } else {
-                isnew = 1;
-                if (tr_aln) tr_aln[t] = -1;
-            }
-            if (tr_node) tr_node[t] = isnew ? creator0 + t : creator_p(A, S)[v];
-        }
-        int ks = warp_incl_max(key, lane);
-        ks = max(ks, carry_key);
-        const int incl = warp_incl_sum(isnew, lane);
-        const int nidx = carry_new + incl - isnew;
-        if (t < qlen) {
-            pv_p(A, S)[t] = isnew ? -1 : v;
-            pkey_p(A, S)[t] = ks;
-            pnew_p(A, S)[t] = nidx;
-            psib_p(A, S)[t] = sibof;
-            if (isnew) atomicAdd(&cnt_p(A, S)[ks], 1);
-            if (sibof >= 0) {
-                const int sb = sib[sibof];
-                for (int x = sibof - (sb >> 4); x <= sibof + (sb & 15); ++x) grow_p(A, S)[x] = 1;
+                if (tr_node) tr_node[t] = isnew[u] ? creator0 + t : creator[v[u]];
             }
         }
-        carry_key = __shfl_sync(FULL, ks, 31);
-        carry_new += __shfl_sync(FULL, incl, 31);
+#pragma unroll
+        for (int u = 0; u < MK; ++u) {
+            const int t = t0 + u * 32 + lane;
+            int ks = warp_incl_max(key[u], lane);
+            ks = max(ks, carry_key);
+            const int incl = warp_incl_sum(isnew[u], lane);
+            const int nidx = carry_new + incl - isnew[u];
+            if (t < qlen) {
+                pv[t] = isnew[u] ? -1 : v[u];
+                pkey[t] = ks;
+                pnew[t] = nidx;
+                psib[t] = sibof[u];
+                if (isnew[u]) atomicAdd(&cnt[ks], 1);
+                if (sibof[u] >= 0) {
+                    const int sb = sib[sibof[u]];
+                    for (int x = sibof[u] - (sb >> 4); x <= sibof[u] + (sb & 15); ++x) grow[x] = 1;
+                }
+            }
+            carry_key = __shfl_sync(FULL, ks, 31);
+            carry_new += __shfl_sync(FULL, incl, 31);
+        }
     }
     const int n_new = carry_new;
     const int N2 = N + n_new;
@@ -224,39 +242,57 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
     /* U2: shift[r] = number of new nodes placed before old row r (exclusive scan of cnt) */
     {
         int carry = 0;
-        for (int r0 = 0; r0 < N; r0 += 32) {
-            const int r = r0 + lane;
-            const int c = r < N ? cnt_p(A, S)[r] : 0;
-            const int incl = warp_incl_sum(c, lane);
-            if (r < N) {
-                const int sh = carry + incl - c;
-                cnt_p(A, S)[r] = sh;
-                srcof_p(A, S)[r + sh] = r;
+        for (int r0 = 0; r0 < N; r0 += 32 * MK) {
+            int c[MK];
+#pragma unroll
+            for (int u = 0; u < MK; ++u) { const int r = r0 + u * 32 + lane; c[u] = r < N ? cnt[r] : 0; }
+#pragma unroll
+            for (int u = 0; u < MK; ++u) {
+                const int r = r0 + u * 32 + lane;
+                const int incl = warp_incl_sum(c[u], lane);
+                if (r < N) {
+                    const int sh = carry + incl - c[u];
+                    cnt[r] = sh;
+                    srcof[r + sh] = r;
+                }
+                carry += __shfl_sync(FULL, incl, 31);
             }
-            carry += __shfl_sync(FULL, incl, 31);
         }
         for (int t = lane; t < qlen; t += 32)
-            if (pv_p(A, S)[t] < 0) srcof_p(A, S)[pkey_p(A, S)[t] + 1 + pnew_p(A, S)[t]] = -(t + 1);
+            if (pv[t] < 0) srcof[pkey[t] + 1 + pnew[t]] = -(t + 1);
     }
     __syncwarp();
 
     /* U3: the path edges u[t-1] -> u[t], t = 0..qlen (u[-1] = source, u[qlen] = sink) */
     int n_new_edges = 0;
-    for (int t = lane; t <= qlen; t += 32) {
-        const int from_old = t == 0 ? 0 : pv_p(A, S)[t - 1];
-        const int to_old = t == qlen ? N - 1 : pv_p(A, S)[t];
-        const int from_new = from_old >= 0 ? from_old + cnt_p(A, S)[from_old] : pkey_p(A, S)[t - 1] + 1 + pnew_p(A, S)[t - 1];
-        const int to_new = to_old >= 0 ? to_old + cnt_p(A, S)[to_old] : pkey_p(A, S)[t] + 1 + pnew_p(A, S)[t];
-        bool found = false;
-        if (from_old >= 0 && to_old >= 0) {
-            const uint32_t o0 = out_off[from_old], o1 = out_off[from_old + 1];
-            for (uint32_t e = o0; e < o1; ++e)
-                if ((int)out_row[e] == to_old) { out_w[e] += 1; found = true; break; }
+    for (int t0 = 0; t0 <= qlen; t0 += 32 * MK) {
+        int from_old[MK], to_old[MK], from_new[MK], to_new[MK];
+        uint32_t o0[MK], o1[MK];
+#pragma unroll
+        for (int u = 0; u < MK; ++u) {
+            const int t = t0 + u * 32 + lane;
+            from_old[u] = to_old[u] = -2; o0[u] = o1[u] = 0; from_new[u] = to_new[u] = 0;
+            if (t <= qlen) {
+                from_old[u] = t == 0 ? 0 : pv[t - 1];
+                to_old[u] = t == qlen ? N - 1 : pv[t];
+                from_new[u] = from_old[u] >= 0 ? from_old[u] + cnt[from_old[u]] : pkey[t - 1] + 1 + pnew[t - 1];
+                to_new[u] = to_old[u] >= 0 ? to_old[u] + cnt[to_old[u]] : pkey[t] + 1 + pnew[t];
+                if (from_old[u] >= 0 && to_old[u] >= 0) { o0[u] = out_off[from_old[u]]; o1[u] = out_off[from_old[u] + 1]; }
+            }
         }
-        if (!found) {
-            ++n_new_edges;
-            if (from_old >= 0) addout_p(A, S)[from_old] = to_new; else nout_p(A, S)[t - 1] = to_new;
-            if (to_old >= 0) addin_p(A, S)[to_old] = from_new; else nin_p(A, S)[t] = from_new;
+#pragma unroll
+        for (int u = 0; u < MK; ++u) {
+            const int t = t0 + u * 32 + lane;
+            if (t <= qlen) {
+                bool found = false;
+                for (uint32_t e = o0[u]; e < o1[u]; ++e)
+                    if ((int)out_row[e] == to_old[u]) { out_w[e] += 1; found = true; break; }
+                if (!found) {
+                    ++n_new_edges;
+                    if (from_old[u] >= 0) addout[from_old[u]] = to_new[u]; else nout[t - 1] = to_new[u];
+                    if (to_old[u] >= 0) addin[to_old[u]] = from_new[u]; else nin[t] = from_new[u];
+                }
+            }
         }
     }
 #pragma unroll
@@ -268,53 +304,70 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
     /* U4: emit the merged graph */
     {
         int carry_in = 0, carry_out = 0;
-        for (int r0 = 0; r0 < N2; r0 += 32) {
-            const int nr = r0 + lane;
-            int din = 0, dout = 0, src = 0;
-            if (nr < N2) {
-                src = srcof_p(A, S)[nr];
-                if (src >= 0) {
-                    din = (int)(in_off[src + 1] - in_off[src]) + (addin_p(A, S)[src] >= 0);
-                    dout = (int)(out_off[src + 1] - out_off[src]) + (addout_p(A, S)[src] >= 0);
-                } else din = dout = 1;
-            }
-            const int iin = warp_incl_sum(din, lane), iout = warp_incl_sum(dout, lane);
-            if (nr < N2) {
-                uint32_t io = carry_in + iin - din, oo = carry_out + iout - dout;
-                n_in_off_p(A, S)[nr] = io;
-                n_out_off_p(A, S)[nr] = oo;
-                if (src >= 0) {
-                    for (uint32_t e = in_off[src]; e < in_off[src + 1]; ++e) {
-                        const int x = (int)in_row[e];
-                        n_in_row_p(A, S)[io++] = x + cnt_p(A, S)[x];
-                    }
-                    if (addin_p(A, S)[src] >= 0) n_in_row_p(A, S)[io++] = addin_p(A, S)[src];
-                    for (uint32_t e = out_off[src]; e < out_off[src + 1]; ++e) {
-                        const int y = (int)out_row[e];
-                        n_out_row_p(A, S)[oo] = y + cnt_p(A, S)[y];
-                        n_out_w_p(A, S)[oo++] = out_w[e];
-                    }
-                    if (addout_p(A, S)[src] >= 0) { n_out_row_p(A, S)[oo] = addout_p(A, S)[src]; n_out_w_p(A, S)[oo++] = 1; }
-                    n_base_p(A, S)[nr] = base[src];
-                    n_sib_p(A, S)[nr] = (uint8_t)(sib[src] + grow_p(A, S)[src]);
-                    n_creator_p(A, S)[nr] = creator_p(A, S)[src];
-                } else {
-                    const int t = -src - 1;
-                    n_in_row_p(A, S)[io] = nin_p(A, S)[t];
-                    n_out_row_p(A, S)[oo] = nout_p(A, S)[t];
-                    n_out_w_p(A, S)[oo] = 1;
-                    n_base_p(A, S)[nr] = q[t];
-                    const int so = psib_p(A, S)[t];
-                    int sb = 0;
-                    if (so >= 0) { const int o = sib[so]; sb = ((o >> 4) + (o & 15) + 1) << 4; }
-                    n_sib_p(A, S)[nr] = (uint8_t)sb;
-                    n_creator_p(A, S)[nr] = creator0 + t;
+        uint32_t *n_in_off = n_in_off_p(A, S), *n_out_off = n_out_off_p(A, S), *n_in_row = n_in_row_p(A, S),
+                 *n_out_row = n_out_row_p(A, S);
+        int32_t *n_out_w = n_out_w_p(A, S), *n_creator = n_creator_p(A, S);
+        uint8_t *n_base = n_base_p(A, S), *n_sib = n_sib_p(A, S);
+        for (int r0 = 0; r0 < N2; r0 += 32 * MK) {
+            int din[MK], dout[MK], src[MK], ai[MK], ao[MK];
+            uint32_t i0[MK], o0[MK];
+#pragma unroll
+            for (int u = 0; u < MK; ++u) {
+                const int nr = r0 + u * 32 + lane;
+                din[u] = dout[u] = 0; src[u] = 0; ai[u] = ao[u] = -1; i0[u] = o0[u] = 0;
+                if (nr < N2) {
+                    src[u] = srcof[nr];
+                    if (src[u] >= 0) {
+                        i0[u] = in_off[src[u]]; o0[u] = out_off[src[u]];
+                        ai[u] = addin[src[u]]; ao[u] = addout[src[u]];
+                        din[u] = (int)(in_off[src[u] + 1] - i0[u]) + (ai[u] >= 0);
+                        dout[u] = (int)(out_off[src[u] + 1] - o0[u]) + (ao[u] >= 0);
+                    } else din[u] = dout[u] = 1;
                 }
             }
-            carry_in += __shfl_sync(FULL, iin, 31);
-            carry_out += __shfl_sync(FULL, iout, 31);
+#pragma unroll
+            for (int u = 0; u < MK; ++u) {
+                const int nr = r0 + u * 32 + lane;
+                const int iin = warp_incl_sum(din[u], lane), iout = warp_incl_sum(dout[u], lane);
+                if (nr < N2) {
+                    uint32_t io = carry_in + iin - din[u], oo = carry_out + iout - dout[u];
+                    n_in_off[nr] = io;
+                    n_out_off[nr] = oo;
+                    const int sr = src[u];
+                    if (sr >= 0) {
+                        const int nin_old = din[u] - (ai[u] >= 0), nout_old = dout[u] - (ao[u] >= 0);
+                        for (int e = 0; e < nin_old; ++e) {
+                            const int x = (int)in_row[i0[u] + e];
+                            n_in_row[io++] = x + cnt[x];
+                        }
+                        if (ai[u] >= 0) n_in_row[io++] = ai[u];
+                        for (int e = 0; e < nout_old; ++e) {
+                            const int y = (int)out_row[o0[u] + e];
+                            n_out_row[oo] = y + cnt[y];
+                            n_out_w[oo++] = out_w[o0[u] + e];
+                        }
+                        if (ao[u] >= 0) { n_out_row[oo] = ao[u]; n_out_w[oo++] = 1; }
+                        n_base[nr] = base[sr];
+                        n_sib[nr] = (uint8_t)(sib[sr] + grow[sr]);
+                        n_creator[nr] = creator[sr];
+                    } else {
+                        const int t = -sr - 1;
+                        n_in_row[io] = nin[t];
+                        n_out_row[oo] = nout[t];
+                        n_out_w[oo] = 1;
+                        n_base[nr] = q[t];
+                        const int so = psib[t];
+                        int sb = 0;
+                        if (so >= 0) { const int o = sib[so]; sb = ((o >> 4) + (o & 15) + 1) << 4; }
+                        n_sib[nr] = (uint8_t)sb;
+                        n_creator[nr] = creator0 + t;
+                    }
+                }
+                carry_in += __shfl_sync(FULL, iin, 31);
+                carry_out += __shfl_sync(FULL, iout, 31);
+            }
         }
-        if (lane == 0) { n_in_off_p(A, S)[N2] = carry_in; n_out_off_p(A, S)[N2] = carry_out; }
+        if (lane == 0) { n_in_off[N2] = carry_in; n_out_off[N2] = carry_out; }
     }
     __syncwarp();
     par ^= 1; N = N2; E = E2;
