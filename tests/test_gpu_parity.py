@@ -102,9 +102,14 @@ def test_unrelated_reads_stress_band_edges(gpu_ctx):
 
 
 @pytest.mark.parametrize("pk", [dict(simd_pn_i16=8, simd_pn_i32=4), dict(simd_pn_i16=32, simd_pn_i32=16),
-                                dict(wb=4, wf=0.0), dict(match=2, mismatch=4), dict(wb=40)])
+                                dict(wb=4, wf=0.0), dict(match=2, mismatch=4), dict(wb=40),
+                                dict(wb=120),                       # band 257..512 cells: the 16-cells-per-lane variant
+                                dict(wb=120, simd_pn_i16=8),        # ... with lanes not aligned to SIMD vectors
+                                dict(wb=300),                       # band > 512 cells: int32 kernel, wide ring
+                                dict(gap_open1=6, gap_ext1=3, gap_open2=30, gap_ext2=2, mismatch=6)])
 def test_other_parameters(built, pk):
-    groups = make_groups(GroupConfig("p_par", 32, 3, 10, 100, 500, "uniform", 0.06, (0.3, 0.35, 0.35)))
+    lo, hi = (600, 1500) if pk.get("wb", 0) >= 120 else (100, 500)     # reads long enough to fill a wide band
+    groups = make_groups(GroupConfig("p_par", 32 if hi == 500 else 12, 3, 10, lo, hi, "uniform", 0.06, (0.3, 0.35, 0.35)))
     packed = pack_groups(groups)
     want = oracle_consensus_batch(packed=packed, trace=True, params=OracleParams(**pk))
     with PoaContext(0, PoaParams(**pk)) as ctx:
