@@ -244,7 +244,9 @@ def main():
         prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(prof):
             try:
-                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+                # ncu --set full capture of the same kernel (profiles/README.md): DRAM bytes per band cell
+                # x the band cells of THIS launch
+                traffic = json.load(open(prof)).get("dram_bytes_per_band_cell") * stats["band_cells"]
             except (OSError, ValueError):
                 traffic = None
         # INT-pipe peak measured live: VIADDMNMX.S16x2 warp-instructions/s x 32 lanes x 2 int16 ops
