@@ -41,6 +41,22 @@ struct GroupInfo {
     int8_t attempt;    // workspace-capacity escalation
 };
 
+/* grow-only device buffer: batches of similar size reuse their allocations */
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
 struct mpoa_ctx {
     int dev = 0;
     int n_sm = 0;
@@ -63,6 +79,8 @@ struct mpoa_ctx {
     long long *d_tr_cells = nullptr;
     uint8_t *d_ws = nullptr;
     size_t ws_bytes = 0;
+    DevBuf b_ascii, b_codes, b_rbo, b_gro, b_region, b_len, b_status, b_queue, b_out_off, b_out;
+    DevBuf b_tr_score, b_tr_bits, b_tr_cells, b_tr_aln, b_tr_node;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t side[16] = {nullptr};
     cudaEvent_t fork_ev = nullptr, join_ev[16] = {nullptr};
@@ -81,16 +99,19 @@ struct mpoa_ctx {
         }                                                                                          \
     } while (0)
 
-static void free_batch(mpoa_ctx *ctx) {
-    cudaFree(ctx->d_codes); cudaFree(ctx->d_rbo); cudaFree(ctx->d_gro); cudaFree(ctx->d_region_off);
-    cudaFree(ctx->d_cons); cudaFree(ctx->d_cons_len); cudaFree(ctx->d_status); cudaFree(ctx->d_queue);
-    cudaFree(ctx->d_tr_score); cudaFree(ctx->d_tr_bits); cudaFree(ctx->d_tr_aln); cudaFree(ctx->d_tr_node);
-    cudaFree(ctx->d_tr_cells);
+static void free_batch(mpoa_ctx *ctx) {   // forgets the uploaded batch; device buffers are kept for reuse
     ctx->d_codes = nullptr; ctx->d_rbo = ctx->d_gro = ctx->d_region_off = nullptr; ctx->d_cons = nullptr;
     ctx->d_cons_len = ctx->d_status = ctx->d_queue = nullptr;
     ctx->d_tr_score = ctx->d_tr_bits = ctx->d_tr_aln = ctx->d_tr_node = nullptr; ctx->d_tr_cells = nullptr;
     ctx->n_groups = ctx->n_reads = ctx->n_bases = 0;
     ctx->ran = false;
+}
+
+static void release_buffers(mpoa_ctx *ctx) {
+    for (DevBuf *b : {&ctx->b_ascii, &ctx->b_codes, &ctx->b_rbo, &ctx->b_gro, &ctx->b_region, &ctx->b_len, &ctx->b_status,
+                      &ctx->b_queue, &ctx->b_out_off, &ctx->b_out, &ctx->b_tr_score, &ctx->b_tr_bits, &ctx->b_tr_cells,
+                      &ctx->b_tr_aln, &ctx->b_tr_node})
+        b->release();
 }
 
 extern "C" int mpoa_abi_version(void) { return MPOA_ABI_VERSION; }
@@ -135,6 +156,7 @@ extern "C" void mpoa_destroy(mpoa_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->dev);
     free_batch(ctx);
+    release_buffers(ctx);
     cudaFree(ctx->d_ws);
     cudaFree(ctx->d_queue_head);
     cudaFree(ctx->d_stats);
@@ -238,17 +260,18 @@ extern "C" int mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups, const int64_t 
 
     cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;
     CK(cudaEventRecord(e0, ctx->stream));
-    uint8_t *d_ascii = nullptr;
     const size_t nb = (size_t)std::max<int64_t>(n_bases, 16);
-    CK(cudaMalloc(&d_ascii, nb));
-    CK(cudaMalloc(&ctx->d_codes, nb));
-    CK(cudaMalloc(&ctx->d_rbo, (n_reads + 1) * sizeof(int64_t)));
-    CK(cudaMalloc(&ctx->d_gro, (n_groups + 1) * sizeof(int64_t)));
-    CK(cudaMalloc(&ctx->d_region_off, (n_groups + 1) * sizeof(int64_t)));
-    CK(cudaMalloc(&ctx->d_cons, nb));
-    CK(cudaMalloc(&ctx->d_cons_len, n_groups * sizeof(int32_t)));
-    CK(cudaMalloc(&ctx->d_status, n_groups * sizeof(int32_t)));
-    CK(cudaMalloc(&ctx->d_queue, n_groups * sizeof(int32_t)));
+    CK(ctx->b_ascii.ensure(nb)); CK(ctx->b_codes.ensure(nb));
+    CK(ctx->b_rbo.ensure((n_reads + 1) * sizeof(int64_t))); CK(ctx->b_gro.ensure((n_groups + 1) * sizeof(int64_t)));
+    CK(ctx->b_region.ensure((n_groups + 1) * sizeof(int64_t)));
+    CK(ctx->b_len.ensure(n_groups * sizeof(int32_t))); CK(ctx->b_status.ensure(n_groups * sizeof(int32_t)));
+    CK(ctx->b_queue.ensure(n_groups * sizeof(int32_t)));
+    uint8_t *d_ascii = (uint8_t *)ctx->b_ascii.p;
+    ctx->d_codes = (uint8_t *)ctx->b_codes.p;
+    ctx->d_rbo = (int64_t *)ctx->b_rbo.p; ctx->d_gro = (int64_t *)ctx->b_gro.p; ctx->d_region_off = (int64_t *)ctx->b_region.p;
+    /* the ASCII input is dead once it is encoded: its buffer becomes the consensus regions */
+    ctx->d_cons = d_ascii;
+    ctx->d_cons_len = (int32_t *)ctx->b_len.p; ctx->d_status = (int32_t *)ctx->b_status.p; ctx->d_queue = (int32_t *)ctx->b_queue.p;
     if (n_bases > 0) CK(cudaMemcpyAsync(d_ascii, bases, n_bases, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_rbo, ctx->h_rbo.data(), (n_reads + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_gro, ctx->h_gro.data(), (n_groups + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -259,18 +282,19 @@ extern "C" int mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups, const int64_t 
     CK(cudaMemcpyAsync(ctx->d_region_off, region.data(), (n_groups + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(launch_encode(d_ascii, ctx->d_codes, n_bases, ctx->stream));
     if (ctx->want_trace) {
-        CK(cudaMalloc(&ctx->d_tr_score, std::max<int64_t>(n_reads, 1) * sizeof(int32_t)));
-        CK(cudaMalloc(&ctx->d_tr_bits, std::max<int64_t>(n_reads, 1) * sizeof(int32_t)));
-        CK(cudaMalloc(&ctx->d_tr_cells, std::max<int64_t>(n_reads, 1) * sizeof(long long)));
-        CK(cudaMalloc(&ctx->d_tr_aln, nb * sizeof(int32_t)));
-        CK(cudaMalloc(&ctx->d_tr_node, nb * sizeof(int32_t)));
+        const size_t nr = (size_t)std::max<int64_t>(n_reads, 1);
+        CK(ctx->b_tr_score.ensure(nr * sizeof(int32_t))); CK(ctx->b_tr_bits.ensure(nr * sizeof(int32_t)));
+        CK(ctx->b_tr_cells.ensure(nr * sizeof(long long)));
+        CK(ctx->b_tr_aln.ensure(nb * sizeof(int32_t))); CK(ctx->b_tr_node.ensure(nb * sizeof(int32_t)));
+        ctx->d_tr_score = (int32_t *)ctx->b_tr_score.p; ctx->d_tr_bits = (int32_t *)ctx->b_tr_bits.p;
+        ctx->d_tr_cells = (long long *)ctx->b_tr_cells.p;
+        ctx->d_tr_aln = (int32_t *)ctx->b_tr_aln.p; ctx->d_tr_node = (int32_t *)ctx->b_tr_node.p;
     }
     CK(cudaEventRecord(e1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     ctx->h2d_ms = ms;
-    cudaFree(d_ascii);
     return MPOA_OK;
 }
 
@@ -662,16 +686,14 @@ extern "C" int mpoa_batch_fetch(mpoa_ctx *ctx, int64_t *cons_off, uint8_t *cons_
     int rc = MPOA_OK;
     if (total > cons_cap || (total > 0 && !cons_buf)) rc = MPOA_ENOSPC;
     else if (total > 0) {
-        int64_t *d_out_off = nullptr;
-        uint8_t *d_out = nullptr;
-        CK(cudaMalloc(&d_out_off, (ng + 1) * sizeof(int64_t)));
-        CK(cudaMalloc(&d_out, total));
+        CK(ctx->b_out_off.ensure((ng + 1) * sizeof(int64_t)));
+        CK(ctx->b_out.ensure(total));
+        int64_t *d_out_off = (int64_t *)ctx->b_out_off.p;
+        uint8_t *d_out = (uint8_t *)ctx->b_out.p;
         CK(cudaMemcpyAsync(d_out_off, cons_off, (ng + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
         CK(launch_gather(ctx->d_cons, ctx->d_region_off, d_out_off, d_out, ng, ctx->stream));
         CK(cudaMemcpyAsync(cons_buf, d_out, total, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        cudaFree(d_out_off);
-        cudaFree(d_out);
         ctx->last.n_kernel_launches += 1;
     }
     if (trace && ctx->want_trace) {
