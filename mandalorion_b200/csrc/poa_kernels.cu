@@ -140,7 +140,7 @@ __host__ __device__ constexpr int variant_warp_words(int wcap) {
 }
 
 template <int V>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (V == 2 ? 4 : V == 3 ? 4 : V == 4 ? 4 : V == 8 ? 3 : 3))
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (V == 2 ? 5 : V == 3 ? 4 : V == 4 ? 4 : V == 8 ? 3 : 3))
 poa_group_kernel(const __grid_constant__ KernelArgs A) {
     extern __shared__ __align__(16) int smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

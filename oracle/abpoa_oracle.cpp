@@ -322,26 +322,44 @@ void align_to_graph(Graph &g, const Par &P, const uint8_t *q, int qlen, DpScratc
             }
             const int *mrow = &P.mat[g.node[node_id].base * 5];
             int32_t *Hr = &S.H[off], *E1r = &S.E1[off], *E2r = &S.E2[off], *F1r = &S.F1[off], *F2r = &S.F2[off];
-            int32_t hh_prev = inf_min, f1 = inf_min, f2 = inf_min;
+            /* pass 1 (independent cells): Hhat = max(M + s, Ein1, Ein2), kept in Hr for now */
             for (int c = 0; c < width; ++c) {
                 const int j = dp_beg + c;
                 const int s = j > 0 ? mrow[q[j - 1]] : 0;
-                int32_t hh = sat((int64_t)S.mx[c] + s, type_min);
-                hh = std::max(hh, std::max(S.ei1[c], S.ei2[c]));
-                if (c == 0) {
-                    f1 = sat((int64_t)inf_min - P.oe1, type_min);
-                    f2 = sat((int64_t)inf_min - P.oe2, type_min);
-                } else {
-                    f1 = std::max(sat((int64_t)hh_prev - P.oe1, type_min), sat((int64_t)f1 - P.e1, type_min));
-                    f2 = std::max(sat((int64_t)hh_prev - P.oe2, type_min), sat((int64_t)f2 - P.e2, type_min));
+                const int32_t m = S.mx[c] < type_min - std::min(s, 0) ? type_min : S.mx[c] + s;   // saturating add
+                Hr[c] = std::max(m, std::max(S.ei1[c], S.ei2[c]));
+            }
+            /* pass 2 (serial along the row): F[c] = max(Hhat[c-1] - oe, F[c-1] - e), saturating */
+            {
+                auto ssub = [type_min](int32_t x, int32_t d) { return x < type_min + d ? type_min : x - d; };
+                int32_t f1 = ssub(inf_min, P.oe1), f2 = ssub(inf_min, P.oe2);
+                F1r[0] = f1; F2r[0] = f2;
+                for (int c = 1; c < width; ++c) {
+                    f1 = std::max(ssub(Hr[c - 1], P.oe1), ssub(f1, P.e1));
+                    f2 = std::max(ssub(Hr[c - 1], P.oe2), ssub(f2, P.e2));
+                    F1r[c] = f1; F2r[c] = f2;
                 }
-                hh_prev = hh;
-                const int32_t h = std::max(hh, std::max(f1, f2));
-                Hr[c] = h; F1r[c] = f1; F2r[c] = f2;
-                E1r[c] = std::max(sat((int64_t)S.ei1[c] - P.e1, type_min), sat((int64_t)h - P.oe1, type_min));
-                E2r[c] = std::max(sat((int64_t)S.ei2[c] - P.e2, type_min), sat((int64_t)h - P.oe2, type_min));
-                if (h > max) { max = h; left_max_i = right_max_i = j; }
-                else if (h == max && !P.opt.single_argmax) right_max_i = j;
+            }
+            /* pass 3 (independent cells): H, Eout */
+            for (int c = 0; c < width; ++c) {
+                const int32_t h = std::max(Hr[c], std::max(F1r[c], F2r[c]));
+                Hr[c] = h;
+                const int32_t a1 = S.ei1[c] < type_min + P.e1 ? type_min : S.ei1[c] - P.e1;
+                const int32_t b1 = h < type_min + P.oe1 ? type_min : h - P.oe1;
+                const int32_t a2 = S.ei2[c] < type_min + P.e2 ? type_min : S.ei2[c] - P.e2;
+                const int32_t b2 = h < type_min + P.oe2 ? type_min : h - P.oe2;
+                E1r[c] = std::max(a1, b1);
+                E2r[c] = std::max(a2, b2);
+            }
+            /* row maximum with its left-most and right-most column */
+            for (int c = 0; c < width; ++c) max = std::max(max, Hr[c]);
+            if (max > inf_min) {
+                for (int c = 0; c < width; ++c) if (Hr[c] == max) { left_max_i = dp_beg + c; break; }
+                if (P.opt.single_argmax) right_max_i = left_max_i;
+                else for (int c = width - 1; c >= 0; --c) if (Hr[c] == max) { right_max_i = dp_beg + c; break; }
+            } else if (!P.opt.single_argmax) {
+                /* nothing above -inf: abPOA's `else if (h == max) right = j` still fires on cells equal to it */
+                for (int c = width - 1; c >= 0; --c) if (Hr[c] == max) { right_max_i = dp_beg + c; break; }
             }
         }
         for (int out_id : g.node[node_id].out_id) {

@@ -9,7 +9,9 @@ from mandalorion_b200.synth import make_groups  # noqa: E402
 cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-from mandalorion_b200.synth import make_packed
+from mandalorion_b200.synth import make_packed, GroupConfig
+if cfg == 'cfgS':   # short isoforms: every band fits 128 cells
+    cfg = GroupConfig('cfgS', n, 10, 50, 500, 1500, 'loguniform', 0.01, (0.30, 0.35, 0.35))
 packed = make_packed(cfg, n)
 ctx = PoaContext(0)
 ctx.upload(*packed)
