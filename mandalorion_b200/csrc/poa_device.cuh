@@ -95,7 +95,7 @@ enum StatIdx { SI_CELLS = 0, SI_INTOPS, SI_FULL, SI_ALN, SI_ALN16, SI_ALN32, SI_
                SI_T_PREP, SI_T_DP, SI_T_TB, SI_T_MERGE, SI_T_CONS, SI_T_BUSY, SI_COUNT };
 
 /* kernel variants: 0 = int32 lanes, any band width (chunks of 32 cells);
- * 2/3/4/8 = packed int16x2, that many 32-bit words (pairs of cells) per lane: band <= 128/192/256/512 */
-constexpr int kVariants[] = {0, 2, 3, 4, 8};
+ * 2/4/8 = packed int16x2, that many 32-bit words (pairs of cells) per lane: band <= 128/256/512 */
+constexpr int kVariants[] = {0, 2, 4, 8};
 
 }  // namespace mpoa

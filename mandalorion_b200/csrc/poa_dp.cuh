@@ -249,30 +249,67 @@ __device__ __forceinline__ uint32_t pack2(int lo, int hi) { return ((uint32_t)lo
 __device__ __forceinline__ int lo16(uint32_t w) { return (int)(short)(w & 0xffffu); }
 __device__ __forceinline__ int hi16(uint32_t w) { return (int)w >> 16; }
 
-/* shared-memory words of one warp: RING rows x 3 arrays x (32*WPL + 2*RING_PAD), the query
- * profile of the rows' current column window (5 bases x 32*WPL words) and ring_info */
+/* shared-memory words of one warp: RINGV rows x 3 arrays x 32*WPL words (lane-stationary slots),
+ * the query profile of the lanes' current columns (5 bases x 32*WPL words) and ring_info */
 template <int WPL>
-__host__ __device__ constexpr int ring16_row_words() { return 32 * WPL + 2 * RING_PAD; }
+__host__ __device__ constexpr int ring16_row_words() { return 32 * WPL; }
 template <int WPL>
 __host__ __device__ constexpr int ring16_rows() { return WPL >= 4 ? 4 : 8; }   // rows kept in shared memory
 template <int WPL>
 __host__ __device__ constexpr int ring16_warp_words() { return ring16_rows<WPL>() * 3 * ring16_row_words<WPL>() + 5 * 32 * WPL + RING * 4; }
 
 template <int WPL>
+__device__ __forceinline__ void ld_words(const uint32_t *p, uint32_t (&v)[WPL]) {
+    if constexpr (WPL == 2) { const uint2 a = *reinterpret_cast<const uint2 *>(p); v[0] = a.x; v[1] = a.y; }
+    else {
+#pragma unroll
+        for (int m = 0; m < WPL; m += 4) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(p + m);
+            v[m] = a.x; v[m + 1] = a.y; v[m + 2] = a.z; v[m + 3] = a.w;
+        }
+    }
+}
+template <int WPL>
+__device__ __forceinline__ void st_words(uint32_t *p, const uint32_t (&v)[WPL]) {
+    if constexpr (WPL == 2) *reinterpret_cast<uint2 *>(p) = make_uint2(v[0], v[1]);
+    else {
+#pragma unroll
+        for (int m = 0; m < WPL; m += 4) *reinterpret_cast<uint4 *>(p + m) = make_uint4(v[m], v[m + 1], v[m + 2], v[m + 3]);
+    }
+}
+
+/*
+ * Lane-stationary packed DP.  Column c of the query always lives in lane (c / CPL) mod 32, word
+ * (c mod CPL) / 2 -- whatever the band start is.  A row's band [dp_beg, hi] (at most 32*CPL cells,
+ * dp_beg a multiple of the SIMD vector length, hence of CPL) therefore occupies a ROTATED run of
+ * lanes starting at lane (dp_beg / CPL) mod 32, and
+ *   - a row whose only predecessor is the previous row (4 of 5 rows) takes H/E1/E2 of that row
+ *     straight from the registers they were computed in: no shared-memory gather, no shifting
+ *     when the band moves (a lane the band start has passed re-binds to the column 32*CPL further
+ *     right and resets its registers to -inf);
+ *   - the shared-memory ring and the query profile are indexed by lane: every lane reads back
+ *     exactly the slots it wrote (no bank conflicts, no __syncwarp between rows);
+ *   - cells outside the band are kept at -inf (a per-lane mask that changes only with the band),
+ *     so neighbours and later rows see what abPOA's band would have shown them.
+ * The insertion recurrence runs over the rotated lane order (one rotate, one 5-step decayed
+ * max-scan, one rotate back).
+ */
+template <int WPL>
 __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, int N, const uint8_t *__restrict__ q,
                                           int qlen, uint32_t *ring, int4 *ring_info, int lane, AlnState &R) {
     constexpr int CPL = 2 * WPL;              // cells per lane
     constexpr int WCAP = 32 * CPL;            // cells per row
-    constexpr int RW = ring16_row_words<WPL>();
-    constexpr int PW = 32 * WPL;              // words of one profile row
+    constexpr int RW = 32 * WPL;              // words of one ring / profile row
     constexpr int RINGV = ring16_rows<WPL>();
+    constexpr int LGC = WPL == 2 ? 2 : WPL == 4 ? 3 : 4;
+    static_assert(WPL == 2 || WPL == 4 || WPL == 8, "words per lane");
     const DevParams &P = A.P;
     const Packed16 &K = A.K;
     const uint32_t *in_off = in_off_p(A, S), *in_row = in_row_p(A, S);
     uint32_t *tb = reinterpret_cast<uint32_t *>(tb_p(A, S));   // words = pairs of int16 cells
     const uint32_t tbcap = (uint32_t)min(A.L.tbcap / 4, (uint64_t)0xfffffff0u);
     lane_width_rule(P, qlen, N, R);
-    if (R.bits != 16) return ST_RETRY_32;     // needs the int32 kernel
+    if (R.bits != 16 || (R.pn & (CPL - 1))) return ST_RETRY_32;   // int32 lanes, or a lane would straddle a band edge
     const int lg = R.lgpn;
     const int w = P.wb < 0 ? qlen : P.wb + (int)__fmul_rn(P.wf, (float)qlen);
     uint32_t tb_used = 0;                     // words
@@ -280,11 +317,48 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
     int err = ST_OK;                          // sticky: checked once per window of 32 rows
 
     const uint32_t NEG2 = K.neg2;
-    const int wl0 = lane * WPL;               // first word of this lane inside a row
-    const int col0 = lane * CPL;              // first cell
-    uint32_t *prof = ring + RINGV * 3 * RW;    // [5][PW] match/mismatch words of the current window
-    /* vector accesses of a lane's WPL words need the pred row shifted by whole lanes */
-    const bool lanes_whole = ((R.pn >> 1) % WPL) == 0;
+    uint32_t *myring = ring + lane * WPL;                       // + (row & (RINGV-1)) * 3*RW + array * RW
+    uint32_t *myprof = ring + RINGV * 3 * RW + lane * WPL;      // + base * RW
+    int4 *rowinfo_g = rowinfo_p(A, S);
+    uint4 *rowtb_g = rowtb_p(A, S);
+
+    /* lane binding (changes only when the band does) */
+    int cur_beg = -1, cur_hi = -1, cur_width = 0;
+    uint32_t cur_stw = 0;
+    int rl = lane, c0 = -1;                   // rotated lane index, first column of this lane
+    uint32_t MK[WPL];                         // 0xffff per in-band cell
+    uint32_t Hp[WPL], E1p[WPL], E2p[WPL];     // the previous row at this lane's columns
+#pragma unroll
+    for (int m = 0; m < WPL; ++m) { MK[m] = 0; Hp[m] = E1p[m] = E2p[m] = NEG2; myprof[4 * RW + m] = 0; }
+
+    auto rebind = [&](int beg, int hi) {
+        cur_beg = beg; cur_hi = hi;
+        cur_width = max(0, hi - beg + 1);
+        if (cur_width > WCAP) { err = ST_RETRY_WIDE; cur_width = WCAP; hi = beg + WCAP - 1; }
+        cur_stw = (uint32_t)(((cur_width + 1) >> 1) + WPL - 1) & ~(uint32_t)(WPL - 1);
+        rl = (lane - (beg >> LGC)) & 31;
+        const int nc0 = beg + rl * CPL;
+        if (nc0 != c0) {
+            c0 = nc0;
+            int qb = q[min(max(c0 - 1, 0), qlen - 1)];
+#pragma unroll
+            for (int m = 0; m < WPL; ++m) {
+                Hp[m] = E1p[m] = E2p[m] = NEG2;
+                /* word m = cells c0+2m, c0+2m+1; cell j consumes q[j-1] */
+                const int qa = qb, qc = q[min(c0 + 2 * m, qlen - 1)];
+                qb = q[min(c0 + 2 * m + 1, qlen - 1)];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int sa = qa >= 4 ? 0 : (qa == b ? P.match : -P.mismatch);
+                    const int sb = qc >= 4 ? 0 : (qc == b ? P.match : -P.mismatch);
+                    myprof[b * RW + m] = pack2(sa, sb);
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < WPL; ++m)
+            MK[m] = (c0 + 2 * m <= hi ? 0xffffu : 0u) | (c0 + 2 * m + 1 <= hi ? 0xffff0000u : 0u);
+    };
 
     /* row 0: the source */
     int4 prev_info;
@@ -293,42 +367,37 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
         const int e = min(qlen, max(0, qlen - rem0) + w);
         const int end_sn = e >> lg;
         const int hi = min(((end_sn + 1) << lg) - 1, qlen);
-        const int width = hi + 1;
-        if (width > WCAP) return ST_RETRY_WIDE;
-        const uint32_t stw = (uint32_t)(((width + 1) >> 1) + WPL - 1) / WPL * WPL;   // stored words per array
-        if (3 * stw > tbcap) return ST_RETRY;
-        uint32_t *Hs = ring + RING_PAD, *E1s = Hs + RW, *E2s = Hs + 2 * RW;
+        if (hi + 1 > WCAP) return ST_RETRY_WIDE;
+        rebind(0, hi);
+        if (3 * cur_stw > tbcap) return ST_RETRY;
 #pragma unroll
         for (int m = 0; m < WPL; ++m) {
-            const int c = col0 + 2 * m;
             int hv[2];
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
-                const int cc = c + t;
+                const int cc = c0 + 2 * m + t;
                 hv[t] = cc == 0 ? 0 : max(max(-(P.o1 + P.e1 * cc), -(P.o2 + P.e2 * cc)), NEG16);
             }
-            const uint32_t hw = pack2(hv[0], hv[1]);
-            const uint32_t e1w = c == 0 ? pack2(-P.oe1, NEG16) : NEG2, e2w = c == 0 ? pack2(-P.oe2, NEG16) : NEG2;
-            Hs[wl0 + m] = hw; E1s[wl0 + m] = e1w; E2s[wl0 + m] = e2w;
-            if ((uint32_t)(wl0 + m) < stw) { tb[wl0 + m] = hw; tb[stw + wl0 + m] = e1w; tb[2 * stw + wl0 + m] = e2w; }
-            prof[4 * PW + wl0 + m] = 0;       // a node base N scores 0 against everything
+            Hp[m] = (pack2(hv[0], hv[1]) & MK[m]) | (NEG2 & ~MK[m]);
+            E1p[m] = (c0 + 2 * m == 0) ? pack2(-P.oe1, NEG16) : NEG2;
+            E2p[m] = (c0 + 2 * m == 0) ? pack2(-P.oe2, NEG16) : NEG2;
+        }
+        st_words<WPL>(myring, Hp); st_words<WPL>(myring + RW, E1p); st_words<WPL>(myring + 2 * RW, E2p);
+        if ((uint32_t)(rl * WPL) < cur_stw) {
+            uint32_t *g = tb + rl * WPL;
+            st_words<WPL>(g, Hp); st_words<WPL>(g + cur_stw, E1p); st_words<WPL>(g + 2 * cur_stw, E2p);
         }
         prev_info = make_int4(0, end_sn, 0, 0);
         if (lane == 0) {
             ring_info[0] = prev_info;
-            rowinfo_p(A, S)[0] = prev_info;
-            rowtb_p(A, S)[0] = make_uint4(0, 2 * stw, 0, 0);
+            rowinfo_g[0] = prev_info;
+            rowtb_g[0] = make_uint4(0, 2 * cur_stw, 0, 0);
         }
-        tb_used = 3 * stw;
-        __syncwarp();
+        tb_used = 3 * cur_stw;
     }
 
-    int prof_beg = -1;                        // band start the profile was built for
-    int4 *rowinfo_g = rowinfo_p(A, S);
-    uint4 *rowtb_g = rowtb_p(A, S);
-
     for (int w0 = 1; w0 < N - 1; w0 += 32) {
-        /* row metadata of 32 rows at once: a = base | flags | npre<<5 | remain<<13 */
+        /* row metadata of 32 rows at once: a = base | flags | simple<<5 | npre<<6 | remain<<14 */
         uint32_t m_a = 0;
         int m_in0 = 0, m_p0 = 0;
         {
@@ -336,28 +405,29 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
             if (r < N - 1) {
                 m_in0 = (int)in_off[r];
                 const int npre = (int)in_off[r + 1] - m_in0;
-                m_a = (meta_p(A, S)[r] & 31u) | ((uint32_t)min(npre, 255) << 5) | ((uint32_t)remain_p(A, S)[r] << 13);
                 m_p0 = npre > 0 ? (int)in_row[m_in0] : 0;
+                const uint32_t simple = (npre == 1 && m_p0 == r - 1) ? 32u : 0u;
+                m_a = (meta_p(A, S)[r] & 31u) | simple | ((uint32_t)min(npre, 255) << 6) | ((uint32_t)remain_p(A, S)[r] << 14);
             }
         }
         const int nrows = min(32, N - 1 - w0);
         for (int l = 0; l < nrows; ++l) {
             const int i = w0 + l;
             const uint32_t ma = __shfl_sync(FULL, m_a, l);
-            const int p0 = __shfl_sync(FULL, m_p0, l);
             const int nbase = ma & META_BASE;
-            const int rem = (int)(ma >> 13);
-            int npre = (ma >> 5) & 255;
-            int in0 = 0;
+            const int rem = (int)(ma >> 14);
+            const bool simple = (ma & 32u) != 0;
+            int npre = 1, in0 = 0, p0 = i - 1;
 
-            /* most rows have ONE predecessor and it is the previous row: straight-line path */
-            const bool simple = npre == 1 && p0 == i - 1;
             int left, right, minb, maxe;
             if (simple) {
                 left = min(N, prev_info.z + 1); right = max(0, prev_info.w + 1);
                 minb = prev_info.x; maxe = prev_info.y;
             } else {
+                __syncwarp();                 // ring_info / traceback rows written by other lanes
+                npre = (ma >> 6) & 255;
                 in0 = __shfl_sync(FULL, m_in0, l);
+                p0 = __shfl_sync(FULL, m_p0, l);
                 if (npre == 255) npre = (int)in_off[i + 1] - in0;
                 left = N; right = 0; minb = INT_MAX; maxe = -1;
                 for (int k = 0; k < npre; ++k) {
@@ -370,92 +440,28 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                 }
             }
             const Band B = make_band(left, right, minb, maxe, rem, qlen, w, lg);
-            int width = B.width;
-            const int dp_beg = B.dp_beg;
-            if (width > WCAP) { err = ST_RETRY_WIDE; width = 0; }
-            const uint32_t stw = (uint32_t)(((width + 1) >> 1) + WPL - 1) / WPL * WPL;
+            if (B.dp_beg != cur_beg || B.hi_cell != cur_hi) rebind(B.dp_beg, B.hi_cell);
+            const int width = cur_width;
+            const uint32_t stw = cur_stw;
             uint32_t tbo = tb_used;
             const bool ovf = tbcap - tb_used < 3 * stw;
             if (ovf) { if (err == ST_OK) err = ST_RETRY; tbo = 0; }
             else tb_used += 3 * stw;
-            RC.add(width, npre);
+            RC.add(B.width, npre);
 
-            /* query profile of the window [dp_beg, dp_beg + WCAP): rebuilt only when the band start
-             * moves (every ~pn rows); prof[b][word] = (s(b, q[j-1]), s(b, q[j])) for the word's cells */
-            if (dp_beg != prof_beg) {
-                prof_beg = dp_beg;
-                __syncwarp();
-#pragma unroll
-                for (int m = 0; m < WPL; ++m) {
-                    const int j0 = dp_beg + col0 + 2 * m;     // the word's first cell; it consumes q[j0-1]
-                    const int qa = q[min(max(j0 - 1, 0), qlen - 1)], qb = q[min(max(j0, 0), qlen - 1)];
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const int sa = qa >= 4 ? 0 : (qa == b ? P.match : -P.mismatch);
-                        const int sb = qb >= 4 ? 0 : (qb == b ? P.match : -P.mismatch);
-                        prof[b * PW + wl0 + m] = pack2(sa, sb);
-                    }
-                }
-                __syncwarp();
-            }
-
-            /* gather the diagonal and the deletion inputs from the predecessors.  A lane's WPL
-             * words map to pred words [wp0, wp0+WPL); with the pred row shifted by whole lanes they
-             * are all inside the pred's band or all outside: one vector load per array (no bank
-             * conflicts), the word left of them comes from the neighbouring lane by shuffle. */
+            /* diagonal and deletion inputs */
             uint32_t M2[WPL], EA[WPL], EB[WPL];
-            auto gather = [&](const uint32_t *Hp, int st, int pw, int shw, bool vec, bool first) {
-                const int wp0 = wl0 + shw;
-                uint32_t hw[WPL], e1w[WPL], e2w[WPL];
-                if (vec) {
-                    const bool in = wp0 >= 0 && wp0 + WPL <= pw;
-                    const uint32_t *src = Hp + (in ? wp0 : 0);
-                    if constexpr (WPL == 2) {
-                        const uint2 a = *reinterpret_cast<const uint2 *>(src);
-                        const uint2 b = *reinterpret_cast<const uint2 *>(src + st);
-                        const uint2 c = *reinterpret_cast<const uint2 *>(src + 2 * st);
-                        hw[0] = a.x; hw[1] = a.y; e1w[0] = b.x; e1w[1] = b.y; e2w[0] = c.x; e2w[1] = c.y;
-                    } else {
-#pragma unroll
-                        for (int m = 0; m < WPL; m += 4) {
-                            const uint4 a = *reinterpret_cast<const uint4 *>(src + m);
-                            const uint4 b = *reinterpret_cast<const uint4 *>(src + st + m);
-                            const uint4 c = *reinterpret_cast<const uint4 *>(src + 2 * st + m);
-                            hw[m] = a.x; hw[m + 1] = a.y; hw[m + 2] = a.z; hw[m + 3] = a.w;
-                            e1w[m] = b.x; e1w[m + 1] = b.y; e1w[m + 2] = b.z; e1w[m + 3] = b.w;
-                            e2w[m] = c.x; e2w[m + 1] = c.y; e2w[m + 2] = c.z; e2w[m + 3] = c.w;
-                        }
-                    }
-                    if (!in) {
-#pragma unroll
-                        for (int m = 0; m < WPL; ++m) { hw[m] = NEG2; e1w[m] = NEG2; e2w[m] = NEG2; }
-                    }
-                } else {
-#pragma unroll
-                    for (int m = 0; m < WPL; ++m) {
-                        const int wp = wp0 + m;
-                        const bool v = (unsigned)wp < (unsigned)pw;
-                        hw[m] = v ? Hp[wp] : NEG2; e1w[m] = v ? Hp[st + wp] : NEG2; e2w[m] = v ? Hp[2 * st + wp] : NEG2;
-                    }
-                }
-                /* word wp0-1: last word of the lane below, or a direct load at lane 0 */
-                uint32_t hl = __shfl_up_sync(FULL, hw[WPL - 1], 1);
-                if (lane == 0) hl = ((unsigned)(wp0 - 1) < (unsigned)pw) ? Hp[wp0 - 1] : NEG2;
-                if (wp0 <= 0) hl = NEG2;
+            if (simple) {
+                /* a predecessor offers nothing right of ITS rounded band end (abPOA only walks the
+                 * overlapping vectors): the first cell past it has no diagonal either */
+                uint32_t hl = __shfl_sync(FULL, Hp[WPL - 1], lane - 1);
+                if (c0 == ((prev_info.y + 1) << lg)) hl = NEG2;
 #pragma unroll
                 for (int m = 0; m < WPL; ++m) {
-                    /* an out-of-band word holds NEG2 in hw/e1w/e2w already; its diagonal must be NEG2 too */
-                    const bool v = (unsigned)(wp0 + m) < (unsigned)pw;
-                    const uint32_t dg = v ? __byte_perm(hl, hw[m], 0x5432) : NEG2;
-                    if (first) { M2[m] = dg; EA[m] = e1w[m]; EB[m] = e2w[m]; }
-                    else { M2[m] = __vmaxs2(M2[m], dg); EA[m] = __vmaxs2(EA[m], e1w[m]); EB[m] = __vmaxs2(EB[m], e2w[m]); }
-                    hl = hw[m];
+                    M2[m] = __byte_perm(hl, Hp[m], 0x5432);
+                    hl = Hp[m];
+                    EA[m] = E1p[m]; EB[m] = E2p[m];
                 }
-            };
-            if (simple) {
-                const int shw = (dp_beg - (prev_info.x << lg)) >> 1;
-                gather(ring + ((i - 1) & (RINGV - 1)) * 3 * RW + RING_PAD, RW,
-                       ((prev_info.y - prev_info.x + 1) << lg) >> 1, shw, lanes_whole, true);
             } else {
 #pragma unroll
                 for (int m = 0; m < WPL; ++m) { M2[m] = NEG2; EA[m] = NEG2; EB[m] = NEG2; }
@@ -463,35 +469,38 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                     const int p = k == 0 ? p0 : (int)in_row[in0 + k];
                     const bool near = i - p < RINGV;
                     const int4 pi = (p == i - 1) ? prev_info : (near ? ring_info[p & (RINGV - 1)] : rowinfo_g[p]);
-                    const int pw = ((pi.y - pi.x + 1) << lg) >> 1;             // words of the pred's rounded band
-                    const int shw = (dp_beg - (pi.x << lg)) >> 1;              // our word 0 = pred word shw
-                    if (near) gather(ring + (p & (RINGV - 1)) * 3 * RW + RING_PAD, RW, pw, shw, lanes_whole, false);
-                    else {
+                    const int d = c0 - (pi.x << lg);          // my first column relative to the pred's band start
+                    bool ok = (unsigned)d < (unsigned)WCAP;   // same column binding as when row p was computed
+                    uint32_t hw[WPL], e1w[WPL], e2w[WPL];
+                    const uint32_t *src = myring + (p & (RINGV - 1)) * 3 * RW;
+                    int st = RW;
+                    if (!near) {
                         const uint4 rt = rowtb_g[p];
-                        const int pst = (int)(rt.y >> 1);
-                        gather(tb + rt.x, pst, min(pw, pst), shw, false, false);
+                        st = (int)(rt.y >> 1);
+                        ok = ok && (d >> 1) + WPL <= st;
+                        src = tb + rt.x + (ok ? (d >> 1) : 0);
+                    }
+                    if (ok) { ld_words<WPL>(src, hw); ld_words<WPL>(src + st, e1w); ld_words<WPL>(src + 2 * st, e2w); }
+                    else {
+#pragma unroll
+                        for (int m = 0; m < WPL; ++m) { hw[m] = NEG2; e1w[m] = NEG2; e2w[m] = NEG2; }
+                    }
+                    uint32_t hl = __shfl_sync(FULL, hw[WPL - 1], lane - 1);
+                    if (c0 == ((pi.y + 1) << lg)) hl = NEG2;   // nothing from p right of its rounded band end
+#pragma unroll
+                    for (int m = 0; m < WPL; ++m) {
+                        M2[m] = __vmaxs2(M2[m], __byte_perm(hl, hw[m], 0x5432));
+                        EA[m] = __vmaxs2(EA[m], e1w[m]); EB[m] = __vmaxs2(EB[m], e2w[m]);
+                        hl = hw[m];
                     }
                 }
             }
             /* first cell of the row's band: no diagonal at all */
-            if (lane == 0) M2[0] = (M2[0] & 0xffff0000u) | (NEG2 & 0xffffu);
+            if (rl == 0) M2[0] = (M2[0] & 0xffff0000u) | (NEG2 & 0xffffu);
 
             /* match/mismatch scores from the profile row of this node's base */
             uint32_t S2[WPL];
-            {
-                const uint32_t *pr = prof + nbase * PW + wl0;
-                if constexpr (WPL == 2) { const uint2 a = *reinterpret_cast<const uint2 *>(pr); S2[0] = a.x; S2[1] = a.y; }
-                else if constexpr (WPL % 4 == 0) {
-#pragma unroll
-                    for (int m = 0; m < WPL; m += 4) {
-                        const uint4 a = *reinterpret_cast<const uint4 *>(pr + m);
-                        S2[m] = a.x; S2[m + 1] = a.y; S2[m + 2] = a.z; S2[m + 3] = a.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int m = 0; m < WPL; ++m) S2[m] = pr[m];
-                }
-            }
+            ld_words<WPL>(myprof + nbase * RW, S2);
 
             uint32_t HH[WPL];
 #pragma unroll
@@ -510,13 +519,15 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
 #pragma unroll
             for (int t = 1; t < CPL; ++t) FL[t] = __viaddmax_s16x2(FL[t - 1], K.nee, X[t - 1]);
             uint32_t T = __viaddmax_s16x2(FL[CPL - 1], K.nee, X[CPL - 1]);
+            /* decayed max-scan over the ROTATED lane order: rotate, scan, rotate back (exclusive) */
+            T = __shfl_sync(FULL, T, lane + lane - rl);          // rotated position `lane` <- lane first+lane
 #pragma unroll
             for (int dd = 0; dd < 5; ++dd) {
                 const uint32_t up = __shfl_up_sync(FULL, T, 1 << dd);
                 T = __viaddmax_s16x2(up, K.dec[dd], T);
             }
-            uint32_t C = __shfl_up_sync(FULL, T, 1);
-            if (lane == 0) C = NEG2;
+            uint32_t C = __shfl_sync(FULL, T, rl - 1);
+            if (rl == 0) C = NEG2;
             uint32_t F1w[WPL], F2w[WPL];
             {
                 uint32_t fa = 0;
@@ -530,67 +541,44 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                 }
             }
 
-            uint32_t Hw[WPL], E1o[WPL], E2o[WPL];
+            /* H, Eout; cells outside the band stay at -inf */
 #pragma unroll
             for (int m = 0; m < WPL; ++m) {
-                Hw[m] = __vimax3_s16x2(HH[m], F1w[m], F2w[m]);
-                E1o[m] = __viaddmax_s16x2(EA[m], K.ne1, __viaddmax_s16x2(Hw[m], K.noe1, NEG2));
-                E2o[m] = __viaddmax_s16x2(EB[m], K.ne2, __viaddmax_s16x2(Hw[m], K.noe2, NEG2));
+                const uint32_t h = __vimax3_s16x2(HH[m], F1w[m], F2w[m]);
+                const uint32_t e1o = __viaddmax_s16x2(EA[m], K.ne1, __viaddmax_s16x2(h, K.noe1, NEG2));
+                const uint32_t e2o = __viaddmax_s16x2(EB[m], K.ne2, __viaddmax_s16x2(h, K.noe2, NEG2));
+                Hp[m] = (h & MK[m]) | (NEG2 & ~MK[m]);
+                E1p[m] = (e1o & MK[m]) | (NEG2 & ~MK[m]);
+                E2p[m] = (e2o & MK[m]) | (NEG2 & ~MK[m]);
             }
 
-            /* ring + HBM stores */
+            /* ring (own slots) + HBM stores (band order: rotated lane rl holds words rl*WPL ...) */
             {
-                uint32_t *Hr = ring + (i & (RINGV - 1)) * 3 * RW + RING_PAD + wl0;
-                uint32_t *g = tb + tbo + wl0;
-                const bool st = !ovf && (uint32_t)wl0 < stw;
-                if constexpr (WPL == 2) {
-                    *reinterpret_cast<uint2 *>(Hr) = make_uint2(Hw[0], Hw[1]);
-                    *reinterpret_cast<uint2 *>(Hr + RW) = make_uint2(E1o[0], E1o[1]);
-                    *reinterpret_cast<uint2 *>(Hr + 2 * RW) = make_uint2(E2o[0], E2o[1]);
-                    if (st) {
-                        *reinterpret_cast<uint2 *>(g) = make_uint2(Hw[0], Hw[1]);
-                        *reinterpret_cast<uint2 *>(g + stw) = make_uint2(E1o[0], E1o[1]);
-                        *reinterpret_cast<uint2 *>(g + 2 * stw) = make_uint2(E2o[0], E2o[1]);
-                    }
-                } else if constexpr (WPL % 4 == 0) {
-#pragma unroll
-                    for (int m = 0; m < WPL; m += 4) {
-                        const uint4 h4 = make_uint4(Hw[m], Hw[m + 1], Hw[m + 2], Hw[m + 3]);
-                        const uint4 a4 = make_uint4(E1o[m], E1o[m + 1], E1o[m + 2], E1o[m + 3]);
-                        const uint4 b4 = make_uint4(E2o[m], E2o[m + 1], E2o[m + 2], E2o[m + 3]);
-                        *reinterpret_cast<uint4 *>(Hr + m) = h4;
-                        *reinterpret_cast<uint4 *>(Hr + RW + m) = a4;
-                        *reinterpret_cast<uint4 *>(Hr + 2 * RW + m) = b4;
-                        if (st) {
-                            *reinterpret_cast<uint4 *>(g + m) = h4;
-                            *reinterpret_cast<uint4 *>(g + stw + m) = a4;
-                            *reinterpret_cast<uint4 *>(g + 2 * stw + m) = b4;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int m = 0; m < WPL; ++m) {
-                        Hr[m] = Hw[m]; Hr[RW + m] = E1o[m]; Hr[2 * RW + m] = E2o[m];
-                        if (st) { g[m] = Hw[m]; g[stw + m] = E1o[m]; g[2 * stw + m] = E2o[m]; }
-                    }
+                uint32_t *Hr = myring + (i & (RINGV - 1)) * 3 * RW;
+                st_words<WPL>(Hr, Hp); st_words<WPL>(Hr + RW, E1p); st_words<WPL>(Hr + 2 * RW, E2p);
+                if (!ovf && (uint32_t)(rl * WPL) < stw) {
+                    uint32_t *g = tb + tbo + rl * WPL;
+                    st_words<WPL>(g, Hp); st_words<WPL>(g + stw, E1p); st_words<WPL>(g + 2 * stw, E2p);
                 }
             }
 
-            /* row maximum with its left-most and right-most column: two keyed warp reductions */
+            /* row maximum with its left-most and right-most column: two keyed warp reductions;
+             * key = H << 16 | column (resp. reversed column) relative to the band start */
             int kr = INT_MIN, kl = INT_MIN;
 #pragma unroll
-            for (int t = 0; t < CPL; ++t) {
-                const int c = col0 + t;
-                const int hv = (t & 1) ? (int)(Hw[t >> 1] & 0xffff0000u) : (int)(Hw[t >> 1] << 16);
-                if (c < width) {
-                    kr = max(kr, hv | c);
-                    kl = max(kl, hv | (0xffff - c));
-                }
+            for (int m = 0; m < WPL; ++m) {
+                const int a = (int)__byte_perm(Hp[m], 2 * m, 0x1054), b = (int)__byte_perm(Hp[m], 2 * m + 1, 0x3254);
+                const int c = (int)__byte_perm(Hp[m], CPL - 1 - 2 * m, 0x1054), d = (int)__byte_perm(Hp[m], CPL - 2 - 2 * m, 0x3254);
+                kr = __vimax3_s32(kr, a, b);
+                kl = __vimax3_s32(kl, c, d);
             }
-            kr = __reduce_max_sync(FULL, kr);
-            kl = __reduce_max_sync(FULL, kl);
+            kr = __reduce_max_sync(FULL, kr + rl * CPL);
+            kl = __reduce_max_sync(FULL, kl + (0xffff - (CPL - 1) - rl * CPL));
             int lpos = -1, rpos = -1;
-            if (width > 0) { rpos = dp_beg + (kr & 0xffff); lpos = dp_beg + (0xffff - (kl & 0xffff)); }
+            if (width > 0) {
+                rpos = cur_beg + (kr & 0xffff); lpos = cur_beg + (0xffff - (kl & 0xffff));
+                if ((kr >> 16) <= NEG16) { lpos = cur_beg; rpos = cur_beg + width - 1; }   // nothing above -inf
+            }
             prev_info = make_int4(B.beg_sn, B.end_sn, lpos, rpos);
             if (lane == 0) {
                 ring_info[i & (RINGV - 1)] = prev_info;
@@ -600,13 +588,12 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
             if (ma & META_TOSINK) {
                 /* H at the last cell of the row: the global best is picked among these after the DP */
                 int last = NEG;
-                bool mine = width == 0 && lane == 0;
+                bool mine = B.width == 0 && lane == 0;
 #pragma unroll
                 for (int t = 0; t < CPL; ++t)
-                    if (col0 + t == width - 1) { last = (t & 1) ? hi16(Hw[t >> 1]) : lo16(Hw[t >> 1]); mine = true; }
+                    if (rl * CPL + t == B.width - 1) { last = (t & 1) ? hi16(Hp[t >> 1]) : lo16(Hp[t >> 1]); mine = true; }
                 if (mine) rowbest_p(A, S)[i] = last;
             }
-            __syncwarp();
         }
         if (err != ST_OK) return err;
     }

@@ -15,6 +15,13 @@
  */
 #include "poa_traceback.cuh"
 
+#ifndef MPOA_V2_BLOCKS
+#define MPOA_V2_BLOCKS 5
+#endif
+#ifndef MPOA_V4_BLOCKS
+#define MPOA_V4_BLOCKS 4
+#endif
+
 namespace mpoa {
 
 /* ------------------------------------------------------------------------------------------ */
@@ -140,7 +147,7 @@ __host__ __device__ constexpr int variant_warp_words(int wcap) {
 }
 
 template <int V>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (V == 2 ? 5 : V == 3 ? 4 : V == 4 ? 4 : V == 8 ? 3 : 3))
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (V == 2 ? MPOA_V2_BLOCKS : V == 4 ? MPOA_V4_BLOCKS : V == 8 ? 3 : 3))
 poa_group_kernel(const __grid_constant__ KernelArgs A) {
     extern __shared__ __align__(16) int smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -251,7 +258,6 @@ static const void *variant_fn() { return reinterpret_cast<const void *>(&poa_gro
 static const void *kernel_of(int variant) {
     switch (variant) {
         case 2: return variant_fn<2>();
-        case 3: return variant_fn<3>();
         case 4: return variant_fn<4>();
         case 8: return variant_fn<8>();
         default: return variant_fn<0>();
@@ -265,7 +271,6 @@ size_t poa_smem_bytes(int variant, int wcap, int warps_per_block) {
     int words;
     switch (variant) {
         case 2: words = variant_warp_words<2>(wcap); break;
-        case 3: words = variant_warp_words<3>(wcap); break;
         case 4: words = variant_warp_words<4>(wcap); break;
         case 8: words = variant_warp_words<8>(wcap); break;
         default: words = variant_warp_words<0>(wcap); break;

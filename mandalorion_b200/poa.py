@@ -14,7 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def library_path():
-    return os.path.join(_HERE, "libmandalorion_poa.so")
+    # MPOA_LIB: developer override to A/B-test another build of the SAME CUDA library
+    return os.environ.get("MPOA_LIB") or os.path.join(_HERE, "libmandalorion_poa.so")
 
 
 class PoaError(RuntimeError):
