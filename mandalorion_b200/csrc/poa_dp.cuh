@@ -278,6 +278,38 @@ __device__ __forceinline__ void st_words(uint32_t *p, const uint32_t (&v)[WPL]) 
     }
 }
 
+/* shared memory by 32-bit address: the row loop never converts generic pointers.  All of them are
+ * volatile, so they keep their program order among themselves. */
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int WPL>
+__device__ __forceinline__ void lds_words(uint32_t a, uint32_t (&v)[WPL]) {
+    if constexpr (WPL == 2) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(a));
+    else {
+#pragma unroll
+        for (int m = 0; m < WPL; m += 4)
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[m]), "=r"(v[m + 1]), "=r"(v[m + 2]), "=r"(v[m + 3]) : "r"(a + 4 * m));
+    }
+}
+template <int WPL>
+__device__ __forceinline__ void sts_words(uint32_t a, const uint32_t (&v)[WPL]) {
+    if constexpr (WPL == 2) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(a), "r"(v[0]), "r"(v[1]));
+    else {
+#pragma unroll
+        for (int m = 0; m < WPL; m += 4)
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a + 4 * m), "r"(v[m]), "r"(v[m + 1]), "r"(v[m + 2]), "r"(v[m + 3]));
+    }
+}
+__device__ __forceinline__ void sts_word(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v)); }
+/* keeps a loop-invariant value in a register (instead of re-deriving it in every row) */
+__device__ __forceinline__ uint32_t pin_reg(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
+/* key of a row-maximum reduction: (16-bit half of h) << 16 | t; SEL picks the half (0x1054 low, 0x3254 high) */
+template <int T>
+__device__ __forceinline__ int key_of(uint32_t h, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(h), "n"(T), "r"(sel));
+    return (int)d;
+}
+
 /*
  * Lane-stationary packed DP.  Column c of the query always lives in lane (c / CPL) mod 32, word
  * (c mod CPL) / 2 -- whatever the band start is.  A row's band [dp_beg, hi] (at most 32*CPL cells,
@@ -291,52 +323,63 @@ __device__ __forceinline__ void st_words(uint32_t *p, const uint32_t (&v)[WPL]) 
  *     exactly the slots it wrote (no bank conflicts, no __syncwarp between rows);
  *   - cells outside the band are kept at -inf (a per-lane mask that changes only with the band),
  *     so neighbours and later rows see what abPOA's band would have shown them.
- * The insertion recurrence runs over the rotated lane order (one rotate, one 5-step decayed
- * max-scan, one rotate back).
+ * The insertion recurrence runs over the rotated lane order: rotate, plain max-scan of the lane
+ * totals with the decay added back (T + lane * decay), rotate back.
+ * Per-row bookkeeping (band vectors, row maxima, traceback offsets) is kept in the registers of
+ * lane (row mod 32) and written to HBM 32 rows at a time.  Warp-wide values are obtained with
+ * REDUX so that the compiler knows they are uniform (no divergence bookkeeping in the row loop).
  */
 template <int WPL>
-__device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, int N, const uint8_t *__restrict__ q,
-                                          int qlen, uint32_t *ring, int4 *ring_info, int lane, AlnState &R) {
+__device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, int N_in, const uint8_t *__restrict__ q,
+                                          int qlen_in, uint32_t *ring, int lane, AlnState &R) {
     constexpr int CPL = 2 * WPL;              // cells per lane
     constexpr int WCAP = 32 * CPL;            // cells per row
     constexpr int RW = 32 * WPL;              // words of one ring / profile row
     constexpr int RINGV = ring16_rows<WPL>();
     constexpr int LGC = WPL == 2 ? 2 : WPL == 4 ? 3 : 4;
+    constexpr int SEG = 4;                    // cells of one insertion fix-up chain
     static_assert(WPL == 2 || WPL == 4 || WPL == 8, "words per lane");
     const DevParams &P = A.P;
     const Packed16 &K = A.K;
+    const int N = __reduce_max_sync(FULL, N_in), qlen = __reduce_max_sync(FULL, qlen_in);   // uniform
     const uint32_t *in_off = in_off_p(A, S), *in_row = in_row_p(A, S);
     uint32_t *tb = reinterpret_cast<uint32_t *>(tb_p(A, S));   // words = pairs of int16 cells
-    const uint32_t tbcap = (uint32_t)min(A.L.tbcap / 4, (uint64_t)0xfffffff0u);
+    const uint32_t tbcap = pin_reg((uint32_t)min(A.L.tbcap / 4, (uint64_t)0xfffff000u));
     lane_width_rule(P, qlen, N, R);
     if (R.bits != 16 || (R.pn & (CPL - 1))) return ST_RETRY_32;   // int32 lanes, or a lane would straddle a band edge
+    if (31 * CPL * max(P.e1, P.e2) > 2700) return ST_RETRY_32;     // head-room of the decay-free scan
     const int lg = R.lgpn;
     const int w = P.wb < 0 ? qlen : P.wb + (int)__fmul_rn(P.wf, (float)qlen);
     uint32_t tb_used = 0;                     // words
-    RowCount RC = {0, 0, 0};
+    uint32_t cells = 0, extra = 0;
     int err = ST_OK;                          // sticky: checked once per window of 32 rows
 
     const uint32_t NEG2 = K.neg2;
-    uint32_t *myring = ring + lane * WPL;                       // + (row & (RINGV-1)) * 3*RW + array * RW
-    uint32_t *myprof = ring + RINGV * 3 * RW + lane * WPL;      // + base * RW
+    const uint32_t ring_a = smem_addr(ring + lane * WPL);                      // + (row & (RINGV-1)) * 3*RW*4 + array * RW*4
+    const uint32_t prof_a = smem_addr(ring + RINGV * 3 * RW + lane * WPL);     // + base * RW*4
     int4 *rowinfo_g = rowinfo_p(A, S);
     uint4 *rowtb_g = rowtb_p(A, S);
+    const uint32_t sel_lo = pin_reg(0x1054u), sel_hi = pin_reg(0x3254u);
+    const uint32_t lane_up = pack2(P.e1 * CPL * lane, P.e2 * CPL * lane);   // lane decays added back before the scan
 
     /* lane binding (changes only when the band does) */
     int cur_beg = -1, cur_hi = -1, cur_width = 0;
     uint32_t cur_stw = 0;
     int rl = lane, c0 = -1;                   // rotated lane index, first column of this lane
+    uint32_t c_dec = 0;                       // -(rl - 1) lane decays: what the scanned total of rotated lane rl-1 loses on its way
     uint32_t MK[WPL];                         // 0xffff per in-band cell
     uint32_t Hp[WPL], E1p[WPL], E2p[WPL];     // the previous row at this lane's columns
 #pragma unroll
-    for (int m = 0; m < WPL; ++m) { MK[m] = 0; Hp[m] = E1p[m] = E2p[m] = NEG2; myprof[4 * RW + m] = 0; }
+    for (int m = 0; m < WPL; ++m) { MK[m] = 0; Hp[m] = E1p[m] = E2p[m] = NEG2; sts_word(prof_a + (4 * RW + m) * 4, 0); }
 
+    auto stw_of = [&](int width) { return (uint32_t)(((width + 1) >> 1) + WPL - 1) & ~(uint32_t)(WPL - 1); };
     auto rebind = [&](int beg, int hi) {
         cur_beg = beg; cur_hi = hi;
         cur_width = max(0, hi - beg + 1);
         if (cur_width > WCAP) { err = ST_RETRY_WIDE; cur_width = WCAP; hi = beg + WCAP - 1; }
-        cur_stw = (uint32_t)(((cur_width + 1) >> 1) + WPL - 1) & ~(uint32_t)(WPL - 1);
+        cur_stw = stw_of(cur_width);
         rl = (lane - (beg >> LGC)) & 31;
+        c_dec = pack2(-P.e1 * CPL * (rl - 1), -P.e2 * CPL * (rl - 1));
         const int nc0 = beg + rl * CPL;
         if (nc0 != c0) {
             c0 = nc0;
@@ -351,7 +394,7 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                 for (int b = 0; b < 4; ++b) {
                     const int sa = qa >= 4 ? 0 : (qa == b ? P.match : -P.mismatch);
                     const int sb = qc >= 4 ? 0 : (qc == b ? P.match : -P.mismatch);
-                    myprof[b * RW + m] = pack2(sa, sb);
+                    sts_word(prof_a + (b * RW + m) * 4, pack2(sa, sb));
                 }
             }
         }
@@ -360,8 +403,10 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
             MK[m] = (c0 + 2 * m <= hi ? 0xffffu : 0u) | (c0 + 2 * m + 1 <= hi ? 0xffff0000u : 0u);
     };
 
+    /* the previous row's band vectors and row-maximum columns (uniform) */
+    int p_bs = 0, p_es = 0, p_l = 0, p_r = 0;
+
     /* row 0: the source */
-    int4 prev_info;
     {
         const int rem0 = remain_p(A, S)[0];
         const int e = min(qlen, max(0, qlen - rem0) + w);
@@ -382,15 +427,14 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
             E1p[m] = (c0 + 2 * m == 0) ? pack2(-P.oe1, NEG16) : NEG2;
             E2p[m] = (c0 + 2 * m == 0) ? pack2(-P.oe2, NEG16) : NEG2;
         }
-        st_words<WPL>(myring, Hp); st_words<WPL>(myring + RW, E1p); st_words<WPL>(myring + 2 * RW, E2p);
+        sts_words<WPL>(ring_a, Hp); sts_words<WPL>(ring_a + RW * 4, E1p); sts_words<WPL>(ring_a + 2 * RW * 4, E2p);
         if ((uint32_t)(rl * WPL) < cur_stw) {
             uint32_t *g = tb + rl * WPL;
             st_words<WPL>(g, Hp); st_words<WPL>(g + cur_stw, E1p); st_words<WPL>(g + 2 * cur_stw, E2p);
         }
-        prev_info = make_int4(0, end_sn, 0, 0);
+        p_bs = 0; p_es = end_sn; p_l = 0; p_r = 0;
         if (lane == 0) {
-            ring_info[0] = prev_info;
-            rowinfo_g[0] = prev_info;
+            rowinfo_g[0] = make_int4(0, end_sn, 0, 0);
             rowtb_g[0] = make_uint4(0, 2 * cur_stw, 0, 0);
         }
         tb_used = 3 * cur_stw;
@@ -410,10 +454,12 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                 m_a = (meta_p(A, S)[r] & 31u) | simple | ((uint32_t)min(npre, 255) << 6) | ((uint32_t)remain_p(A, S)[r] << 14);
             }
         }
+        /* results of the window's rows, row w0+l in lane l: (beg_sn | end_sn<<16), (lpos+1 | rpos+1 << 16), tb offset */
+        uint32_t d_a = 0, d_b = 0, d_tbo = 0;
         const int nrows = min(32, N - 1 - w0);
         for (int l = 0; l < nrows; ++l) {
             const int i = w0 + l;
-            const uint32_t ma = __shfl_sync(FULL, m_a, l);
+            const uint32_t ma = __reduce_or_sync(FULL, lane == l ? m_a : 0u);
             const int nbase = ma & META_BASE;
             const int rem = (int)(ma >> 14);
             const bool simple = (ma & 32u) != 0;
@@ -421,10 +467,10 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
 
             int left, right, minb, maxe;
             if (simple) {
-                left = min(N, prev_info.z + 1); right = max(0, prev_info.w + 1);
-                minb = prev_info.x; maxe = prev_info.y;
+                left = min(N, p_l + 1); right = max(0, p_r + 1);
+                minb = p_bs; maxe = p_es;
             } else {
-                __syncwarp();                 // ring_info / traceback rows written by other lanes
+                __syncwarp();                 // rows of earlier windows / traceback rows written by other lanes
                 npre = (ma >> 6) & 255;
                 in0 = __shfl_sync(FULL, m_in0, l);
                 p0 = __shfl_sync(FULL, m_p0, l);
@@ -432,22 +478,29 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                 left = N; right = 0; minb = INT_MAX; maxe = -1;
                 for (int k = 0; k < npre; ++k) {
                     const int p = k == 0 ? p0 : (int)in_row[in0 + k];
-                    const int4 pi = (p == i - 1) ? prev_info : ((i - p < RINGV) ? ring_info[p & (RINGV - 1)] : rowinfo_g[p]);
-                    left = min(left, pi.z + 1);
-                    right = max(right, pi.w + 1);
-                    minb = min(minb, pi.x);
-                    maxe = max(maxe, pi.y);
+                    int bs, es, pl, pr;
+                    if (p == i - 1) { bs = p_bs; es = p_es; pl = p_l; pr = p_r; }
+                    else if (p >= w0) {
+                        const uint32_t a = __shfl_sync(FULL, d_a, p - w0), b = __shfl_sync(FULL, d_b, p - w0);
+                        bs = (int)(a & 0xffff); es = (int)(a >> 16); pl = (int)(b & 0xffff) - 1; pr = (int)(b >> 16) - 1;
+                    } else { const int4 pi = rowinfo_g[p]; bs = pi.x; es = pi.y; pl = pi.z; pr = pi.w; }
+                    left = min(left, pl + 1);
+                    right = max(right, pr + 1);
+                    minb = min(minb, bs);
+                    maxe = max(maxe, es);
                 }
             }
             const Band B = make_band(left, right, minb, maxe, rem, qlen, w, lg);
             if (B.dp_beg != cur_beg || B.hi_cell != cur_hi) rebind(B.dp_beg, B.hi_cell);
-            const int width = cur_width;
+            /* match/mismatch scores of this lane's cells against the node's base (after a re-bind:
+             * the lane's profile slots may just have been rewritten) */
+            uint32_t S2[WPL];
+            lds_words<WPL>(prof_a + nbase * (RW * 4), S2);
             const uint32_t stw = cur_stw;
-            uint32_t tbo = tb_used;
-            const bool ovf = tbcap - tb_used < 3 * stw;
-            if (ovf) { if (err == ST_OK) err = ST_RETRY; tbo = 0; }
-            else tb_used += 3 * stw;
-            RC.add(B.width, npre);
+            const uint32_t tbo = tb_used;
+            const bool st_ok = tbo + 3 * stw <= tbcap;
+            if (st_ok) tb_used = tbo + 3 * stw; else if (err == ST_OK) err = ST_RETRY;
+            cells += B.width;
 
             /* diagonal and deletion inputs */
             uint32_t M2[WPL], EA[WPL], EB[WPL];
@@ -455,7 +508,7 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                 /* a predecessor offers nothing right of ITS rounded band end (abPOA only walks the
                  * overlapping vectors): the first cell past it has no diagonal either */
                 uint32_t hl = __shfl_sync(FULL, Hp[WPL - 1], lane - 1);
-                if (c0 == ((prev_info.y + 1) << lg)) hl = NEG2;
+                if (c0 == ((p_es + 1) << lg)) hl = NEG2;
 #pragma unroll
                 for (int m = 0; m < WPL; ++m) {
                     M2[m] = __byte_perm(hl, Hp[m], 0x5432);
@@ -463,30 +516,40 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                     EA[m] = E1p[m]; EB[m] = E2p[m];
                 }
             } else {
+                extra += (uint32_t)max(0, npre - 1) * B.width;
 #pragma unroll
                 for (int m = 0; m < WPL; ++m) { M2[m] = NEG2; EA[m] = NEG2; EB[m] = NEG2; }
                 for (int k = 0; k < npre; ++k) {
                     const int p = k == 0 ? p0 : (int)in_row[in0 + k];
+                    int bs, es;
+                    uint32_t ptbo = 0;
+                    int pst = 0;              // words per array of the stored row
+                    if (p >= w0) {
+                        const uint32_t a = __shfl_sync(FULL, d_a, p - w0);
+                        ptbo = __shfl_sync(FULL, d_tbo, p - w0);
+                        if (p == i - 1) { bs = p_bs; es = p_es; } else { bs = (int)(a & 0xffff); es = (int)(a >> 16); }
+                        pst = (int)stw_of(min(WCAP, max(0, min(((es + 1) << lg) - 1, qlen) - (bs << lg) + 1)));
+                    } else if (p == i - 1) { bs = p_bs; es = p_es; }
+                    else { const int4 pi = rowinfo_g[p]; bs = pi.x; es = pi.y; }
                     const bool near = i - p < RINGV;
-                    const int4 pi = (p == i - 1) ? prev_info : (near ? ring_info[p & (RINGV - 1)] : rowinfo_g[p]);
-                    const int d = c0 - (pi.x << lg);          // my first column relative to the pred's band start
+                    const int d = c0 - (bs << lg);            // my first column relative to the pred's band start
                     bool ok = (unsigned)d < (unsigned)WCAP;   // same column binding as when row p was computed
                     uint32_t hw[WPL], e1w[WPL], e2w[WPL];
-                    const uint32_t *src = myring + (p & (RINGV - 1)) * 3 * RW;
-                    int st = RW;
-                    if (!near) {
-                        const uint4 rt = rowtb_g[p];
-                        st = (int)(rt.y >> 1);
-                        ok = ok && (d >> 1) + WPL <= st;
-                        src = tb + rt.x + (ok ? (d >> 1) : 0);
+                    if (near) {
+                        const uint32_t a = ring_a + (p & (RINGV - 1)) * (3 * RW * 4);
+                        lds_words<WPL>(a, hw); lds_words<WPL>(a + RW * 4, e1w); lds_words<WPL>(a + 2 * RW * 4, e2w);
+                    } else {
+                        if (p < w0) { const uint4 rt = rowtb_g[p]; ptbo = rt.x; pst = (int)(rt.y >> 1); }
+                        ok = ok && (d >> 1) + WPL <= pst;
+                        const uint32_t *src = tb + ptbo + (ok ? (d >> 1) : 0);
+                        if (ok) { ld_words<WPL>(src, hw); ld_words<WPL>(src + pst, e1w); ld_words<WPL>(src + 2 * pst, e2w); }
                     }
-                    if (ok) { ld_words<WPL>(src, hw); ld_words<WPL>(src + st, e1w); ld_words<WPL>(src + 2 * st, e2w); }
-                    else {
+                    if (!ok) {
 #pragma unroll
                         for (int m = 0; m < WPL; ++m) { hw[m] = NEG2; e1w[m] = NEG2; e2w[m] = NEG2; }
                     }
                     uint32_t hl = __shfl_sync(FULL, hw[WPL - 1], lane - 1);
-                    if (c0 == ((pi.y + 1) << lg)) hl = NEG2;   // nothing from p right of its rounded band end
+                    if (c0 == ((es + 1) << lg)) hl = NEG2;   // nothing from p right of its rounded band end
 #pragma unroll
                     for (int m = 0; m < WPL; ++m) {
                         M2[m] = __vmaxs2(M2[m], __byte_perm(hl, hw[m], 0x5432));
@@ -497,10 +560,6 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
             }
             /* first cell of the row's band: no diagonal at all */
             if (rl == 0) M2[0] = (M2[0] & 0xffff0000u) | (NEG2 & 0xffffu);
-
-            /* match/mismatch scores from the profile row of this node's base */
-            uint32_t S2[WPL];
-            ld_words<WPL>(myprof + nbase * RW, S2);
 
             uint32_t HH[WPL];
 #pragma unroll
@@ -519,21 +578,22 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
 #pragma unroll
             for (int t = 1; t < CPL; ++t) FL[t] = __viaddmax_s16x2(FL[t - 1], K.nee, X[t - 1]);
             uint32_t T = __viaddmax_s16x2(FL[CPL - 1], K.nee, X[CPL - 1]);
-            /* decayed max-scan over the ROTATED lane order: rotate, scan, rotate back (exclusive) */
-            T = __shfl_sync(FULL, T, lane + lane - rl);          // rotated position `lane` <- lane first+lane
+            /* max-scan over the ROTATED lane order.  With lane * decay added back the decayed scan is
+             * a plain running maximum; C = what reaches this lane's first cell from the lanes before */
+            T = __vadd2(__shfl_sync(FULL, T, lane + lane - rl), lane_up);
 #pragma unroll
-            for (int dd = 0; dd < 5; ++dd) {
-                const uint32_t up = __shfl_up_sync(FULL, T, 1 << dd);
-                T = __viaddmax_s16x2(up, K.dec[dd], T);
-            }
-            uint32_t C = __shfl_sync(FULL, T, rl - 1);
+            for (int dd = 0; dd < 5; ++dd) T = __vmaxs2(T, __shfl_up_sync(FULL, T, 1 << dd));
+            uint32_t C = __vadd2(__shfl_sync(FULL, T, rl - 1), c_dec);
             if (rl == 0) C = NEG2;
+            /* F of the lane's cells: every SEG-th cell directly, the others by the recurrence */
             uint32_t F1w[WPL], F2w[WPL];
             {
-                uint32_t fa = 0;
+                uint32_t fa = 0, ff = 0;
 #pragma unroll
                 for (int t = 0; t < CPL; ++t) {
-                    const uint32_t ff = __viaddmax_s16x2(C, K.tdec[t], FL[t]);
+                    if (t == 0) ff = __vmaxs2(C, NEG2);
+                    else if (t % SEG == 0) ff = __viaddmax_s16x2(C, K.tdec[t], FL[t]);
+                    else ff = __viaddmax_s16x2(ff, K.nee, X[t - 1]);
                     if (t & 1) {
                         F1w[t >> 1] = __byte_perm(fa, ff, 0x5410);
                         F2w[t >> 1] = __byte_perm(fa, ff, 0x7632);
@@ -541,49 +601,72 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                 }
             }
 
-            /* H, Eout; cells outside the band stay at -inf */
+            /* H; cells outside the band stay at -inf */
 #pragma unroll
             for (int m = 0; m < WPL; ++m) {
                 const uint32_t h = __vimax3_s16x2(HH[m], F1w[m], F2w[m]);
-                const uint32_t e1o = __viaddmax_s16x2(EA[m], K.ne1, __viaddmax_s16x2(h, K.noe1, NEG2));
-                const uint32_t e2o = __viaddmax_s16x2(EB[m], K.ne2, __viaddmax_s16x2(h, K.noe2, NEG2));
                 Hp[m] = (h & MK[m]) | (NEG2 & ~MK[m]);
+            }
+            /* row maximum with its left-most and right-most column: two keyed warp reductions;
+             * key = H << 16 | column (resp. reversed column) relative to the band start */
+            int kr, kl;
+            {
+                int r0 = key_of<0>(Hp[0], sel_lo), r1 = key_of<1>(Hp[0], sel_hi);
+                int l0 = key_of<CPL - 1>(Hp[0], sel_lo), l1 = key_of<CPL - 2>(Hp[0], sel_hi);
+                kr = max(r0, r1); kl = max(l0, l1);
+                if constexpr (WPL >= 2) {
+                    kr = __vimax3_s32(kr, key_of<2>(Hp[1], sel_lo), key_of<3>(Hp[1], sel_hi));
+                    kl = __vimax3_s32(kl, key_of<CPL - 3>(Hp[1], sel_lo), key_of<CPL - 4>(Hp[1], sel_hi));
+                }
+                if constexpr (WPL >= 4) {
+                    kr = __vimax3_s32(kr, key_of<4>(Hp[2], sel_lo), key_of<5>(Hp[2], sel_hi));
+                    kl = __vimax3_s32(kl, key_of<CPL - 5>(Hp[2], sel_lo), key_of<CPL - 6>(Hp[2], sel_hi));
+                    kr = __vimax3_s32(kr, key_of<6>(Hp[3], sel_lo), key_of<7>(Hp[3], sel_hi));
+                    kl = __vimax3_s32(kl, key_of<CPL - 7>(Hp[3], sel_lo), key_of<CPL - 8>(Hp[3], sel_hi));
+                }
+                if constexpr (WPL >= 8) {
+                    kr = __vimax3_s32(kr, key_of<8>(Hp[4], sel_lo), key_of<9>(Hp[4], sel_hi));
+                    kl = __vimax3_s32(kl, key_of<CPL - 9>(Hp[4], sel_lo), key_of<CPL - 10>(Hp[4], sel_hi));
+                    kr = __vimax3_s32(kr, key_of<10>(Hp[5], sel_lo), key_of<11>(Hp[5], sel_hi));
+                    kl = __vimax3_s32(kl, key_of<CPL - 11>(Hp[5], sel_lo), key_of<CPL - 12>(Hp[5], sel_hi));
+                    kr = __vimax3_s32(kr, key_of<12>(Hp[6], sel_lo), key_of<13>(Hp[6], sel_hi));
+                    kl = __vimax3_s32(kl, key_of<CPL - 13>(Hp[6], sel_lo), key_of<CPL - 14>(Hp[6], sel_hi));
+                    kr = __vimax3_s32(kr, key_of<14>(Hp[7], sel_lo), key_of<15>(Hp[7], sel_hi));
+                    kl = __vimax3_s32(kl, key_of<CPL - 15>(Hp[7], sel_lo), key_of<CPL - 16>(Hp[7], sel_hi));
+                }
+            }
+            kr = __reduce_max_sync(FULL, kr + rl * CPL);
+            kl = __reduce_max_sync(FULL, kl + (0xffff - (CPL - 1) - rl * CPL));
+
+            /* Eout (deletion offers to the successors), masked like H */
+#pragma unroll
+            for (int m = 0; m < WPL; ++m) {
+                const uint32_t e1o = __viaddmax_s16x2(EA[m], K.ne1, __viaddmax_s16x2(Hp[m], K.noe1, NEG2));
+                const uint32_t e2o = __viaddmax_s16x2(EB[m], K.ne2, __viaddmax_s16x2(Hp[m], K.noe2, NEG2));
                 E1p[m] = (e1o & MK[m]) | (NEG2 & ~MK[m]);
                 E2p[m] = (e2o & MK[m]) | (NEG2 & ~MK[m]);
             }
 
             /* ring (own slots) + HBM stores (band order: rotated lane rl holds words rl*WPL ...) */
             {
-                uint32_t *Hr = myring + (i & (RINGV - 1)) * 3 * RW;
-                st_words<WPL>(Hr, Hp); st_words<WPL>(Hr + RW, E1p); st_words<WPL>(Hr + 2 * RW, E2p);
-                if (!ovf && (uint32_t)(rl * WPL) < stw) {
+                const uint32_t ra = ring_a + (i & (RINGV - 1)) * (3 * RW * 4);
+                sts_words<WPL>(ra, Hp); sts_words<WPL>(ra + RW * 4, E1p); sts_words<WPL>(ra + 2 * RW * 4, E2p);
+                if (st_ok && (uint32_t)(rl * WPL) < stw) {
                     uint32_t *g = tb + tbo + rl * WPL;
                     st_words<WPL>(g, Hp); st_words<WPL>(g + stw, E1p); st_words<WPL>(g + 2 * stw, E2p);
                 }
             }
 
-            /* row maximum with its left-most and right-most column: two keyed warp reductions;
-             * key = H << 16 | column (resp. reversed column) relative to the band start */
-            int kr = INT_MIN, kl = INT_MIN;
-#pragma unroll
-            for (int m = 0; m < WPL; ++m) {
-                const int a = (int)__byte_perm(Hp[m], 2 * m, 0x1054), b = (int)__byte_perm(Hp[m], 2 * m + 1, 0x3254);
-                const int c = (int)__byte_perm(Hp[m], CPL - 1 - 2 * m, 0x1054), d = (int)__byte_perm(Hp[m], CPL - 2 - 2 * m, 0x3254);
-                kr = __vimax3_s32(kr, a, b);
-                kl = __vimax3_s32(kl, c, d);
-            }
-            kr = __reduce_max_sync(FULL, kr + rl * CPL);
-            kl = __reduce_max_sync(FULL, kl + (0xffff - (CPL - 1) - rl * CPL));
             int lpos = -1, rpos = -1;
-            if (width > 0) {
+            if (cur_width > 0) {
                 rpos = cur_beg + (kr & 0xffff); lpos = cur_beg + (0xffff - (kl & 0xffff));
-                if ((kr >> 16) <= NEG16) { lpos = cur_beg; rpos = cur_beg + width - 1; }   // nothing above -inf
+                if ((kr >> 16) <= NEG16) { lpos = cur_beg; rpos = cur_beg + cur_width - 1; }   // nothing above -inf
             }
-            prev_info = make_int4(B.beg_sn, B.end_sn, lpos, rpos);
-            if (lane == 0) {
-                ring_info[i & (RINGV - 1)] = prev_info;
-                rowinfo_g[i] = prev_info;
-                rowtb_g[i] = make_uint4(tbo, 2 * stw, (uint32_t)p0, (uint32_t)nbase);
+            p_bs = B.beg_sn; p_es = B.end_sn; p_l = lpos; p_r = rpos;
+            if (lane == l) {
+                d_a = (uint32_t)B.beg_sn | ((uint32_t)B.end_sn << 16);
+                d_b = (uint32_t)(lpos + 1) | ((uint32_t)(rpos + 1) << 16);
+                d_tbo = tbo;
             }
             if (ma & META_TOSINK) {
                 /* H at the last cell of the row: the global best is picked among these after the DP */
@@ -595,10 +678,18 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                 if (mine) rowbest_p(A, S)[i] = last;
             }
         }
+        /* the window's bookkeeping, one row per lane */
+        if (lane < nrows) {
+            const int bs = (int)(d_a & 0xffff), es = (int)(d_a >> 16);
+            const int wd = min(WCAP, max(0, min(((es + 1) << lg) - 1, qlen) - (bs << lg) + 1));
+            rowinfo_g[w0 + lane] = make_int4(bs, es, (int)(d_b & 0xffff) - 1, (int)(d_b >> 16) - 1);
+            rowtb_g[w0 + lane] = make_uint4(d_tbo, 2 * stw_of(wd), (uint32_t)m_p0, m_a & META_BASE);
+        }
+        __syncwarp();
         if (err != ST_OK) return err;
     }
     R.tbbytes = (unsigned long long)tb_used * 4;
-    RC.flush(R, qlen);
+    R.cells = cells; R.intops = 17ull * cells + 3ull * extra; R.full = (unsigned long long)(N - 2) * (qlen + 1);
     __syncwarp();
     pick_best(A, S, N, qlen, R);
     return ST_OK;

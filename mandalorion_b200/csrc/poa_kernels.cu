@@ -102,7 +102,7 @@ __device__ __forceinline__ int process_group(const KernelArgs &A, int slot, int 
         AlnState R;
         int rc;
         if constexpr (V == 0) rc = dp_align32(A, S, N, seq, len, ring, ring_info, lane, R);
-        else rc = dp_align16<V>(A, S, N, seq, len, reinterpret_cast<uint32_t *>(ring), ring_info, lane, R);
+        else rc = dp_align16<V>(A, S, N, seq, len, reinterpret_cast<uint32_t *>(ring), lane, R);
         if (rc != ST_OK) return rc;
         tk0 = clock64();
         st[SI_T_DP] += tk0 - tk1;
