@@ -64,7 +64,7 @@ __global__ void encode_bases_kernel(const uint8_t *__restrict__ ascii, uint8_t *
 
 template <int V>
 __device__ __forceinline__ int process_group(const KernelArgs &A, int slot, int g, int *ring, int4 *ring_info, int lane,
-                                             unsigned long long *st) {
+                                             unsigned long long *st /* per-warp counters in shared memory, lane 0 only */) {
     const int64_t r0 = A.group_read_off[g], r1 = A.group_read_off[g + 1];
     if (r1 <= r0) return ST_EMPTY;
     const int64_t gbase = A.read_off[r0];
@@ -98,17 +98,17 @@ __device__ __forceinline__ int process_group(const KernelArgs &A, int slot, int 
         long long tk0 = clock64();
         remain_pass(A, S, N, lane);
         long long tk1 = clock64();
-        st[SI_T_PREP] += tk1 - tk0;
+        if (lane == 0) st[SI_T_PREP] += tk1 - tk0;
         AlnState R;
         int rc;
         if constexpr (V == 0) rc = dp_align32(A, S, N, seq, len, ring, ring_info, lane, R);
         else rc = dp_align16<V>(A, S, N, seq, len, reinterpret_cast<uint32_t *>(ring), lane, R);
         if (rc != ST_OK) return rc;
         tk0 = clock64();
-        st[SI_T_DP] += tk0 - tk1;
-        st[SI_CELLS] += R.cells; st[SI_INTOPS] += R.intops; st[SI_FULL] += R.full; st[SI_ALN] += 1;
-        st[R.bits == 16 ? SI_ALN16 : SI_ALN32] += 1; st[SI_TB] += R.tbbytes;
         if (lane == 0) {
+            st[SI_T_DP] += tk0 - tk1;
+            st[SI_CELLS] += R.cells; st[SI_INTOPS] += R.intops; st[SI_FULL] += R.full; st[SI_ALN] += 1;
+            st[R.bits == 16 ? SI_ALN16 : SI_ALN32] += 1; st[SI_TB] += R.tbbytes;
             if (A.tr_score) A.tr_score[r] = R.best_score;
             if (A.tr_bits) A.tr_bits[r] = R.bits;
             if (A.tr_cells) A.tr_cells[r] = (long long)R.cells;
@@ -120,11 +120,11 @@ __device__ __forceinline__ int process_group(const KernelArgs &A, int slot, int 
         __syncwarp();
         if (!ok) return ST_EMPTY;
         tk1 = clock64();
-        st[SI_T_TB] += tk1 - tk0;
+        if (lane == 0) st[SI_T_TB] += tk1 - tk0;
         const int mrc = merge_read(A, S, par, N, E, seq, len, creator0, tr_aln, tr_node, lane);
         if (mrc != ST_OK) return mrc;
         S = make_slot(A, slot, par);
-        st[SI_T_MERGE] += clock64() - tk1;
+        if (lane == 0) st[SI_T_MERGE] += clock64() - tk1;
     }
     if (N <= 2) return ST_EMPTY;
     const long long tc0 = clock64();
@@ -136,14 +136,14 @@ __device__ __forceinline__ int process_group(const KernelArgs &A, int slot, int 
     clen = __shfl_sync(FULL, clen, 0);
     __syncwarp();
     if (clen < 0) return ST_RETRY;
-    if (lane == 0) A.cons_len[g] = clen;
-    st[SI_T_CONS] += clock64() - tc0;
+    if (lane == 0) { A.cons_len[g] = clen; st[SI_T_CONS] += clock64() - tc0; }
     return ST_OK;
 }
 
 template <int V>
 __host__ __device__ constexpr int variant_warp_words(int wcap) {
-    return V == 0 ? RING * 3 * wcap + RING * 4 : ring16_warp_words<(V == 0 ? 2 : V)>();
+    /* + 32 words: the warp's work counters (SI_COUNT x u64) */
+    return (V == 0 ? RING * 3 * wcap + RING * 4 : ring16_warp_words<(V == 0 ? 2 : V)>()) + 32;
 }
 
 template <int V>
@@ -153,11 +153,12 @@ poa_group_kernel(const __grid_constant__ KernelArgs A) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per_warp = variant_warp_words<V>(A.wcap);
     int *ring = smem + warp * per_warp;
-    int4 *ring_info = reinterpret_cast<int4 *>(ring + per_warp - RING * 4);
+    int4 *ring_info = reinterpret_cast<int4 *>(ring + per_warp - 32 - RING * 4);   // int32 variant only
+    /* work counters of the group in flight: shared memory, touched by lane 0 only (they used to sit
+     * in 26 registers across the DP row loop) */
+    unsigned long long *gst = reinterpret_cast<unsigned long long *>(ring + per_warp - 32);
+    static_assert(SI_COUNT <= 16, "counter block");
     const int slot = blockIdx.x * (blockDim.x >> 5) + warp;
-    unsigned long long st[SI_COUNT];
-#pragma unroll
-    for (int k = 0; k < SI_COUNT; ++k) st[k] = 0;
     int src = -1;   // -1: own queue, k >= 0: steal queue k
     for (;;) {
         int qi = 0, g = -1;
@@ -170,26 +171,24 @@ poa_group_kernel(const __grid_constant__ KernelArgs A) {
             if (++src >= A.n_steal) break;
         }
         if (g < 0) break;
-        unsigned long long gst[SI_COUNT];
+        if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < SI_COUNT; ++k) gst[k] = 0;
+            for (int k = 0; k < SI_COUNT; ++k) gst[k] = 0;
+        }
         const long long tg0 = clock64();
-        const int rc = process_group<V>(A, slot, g, ring, ring_info, lane, gst);
-        gst[SI_T_BUSY] += clock64() - tg0;
+        int rc;
+        if constexpr (V == 0) rc = process_group<V>(A, slot, g, ring, ring_info, lane, gst);
+        else rc = process_group<V>(A, slot, g, ring, nullptr, lane, gst);
         if (lane == 0) {
             A.status[g] = rc;
             if (rc != ST_OK) A.cons_len[g] = 0;
-        }
-        if (rc != ST_RETRY && rc != ST_RETRY_WIDE && rc != ST_RETRY_32) {
-#pragma unroll
-            for (int k = 0; k < SI_COUNT; ++k) st[k] += gst[k];
+            if (rc != ST_RETRY && rc != ST_RETRY_WIDE && rc != ST_RETRY_32) {
+                gst[SI_T_BUSY] += clock64() - tg0;
+                for (int k = 0; k < SI_COUNT; ++k)
+                    if (gst[k]) atomicAdd(A.stats + k, gst[k]);
+            }
         }
         __syncwarp();
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < SI_COUNT; ++k)
-            if (st[k]) atomicAdd(A.stats + k, st[k]);
     }
 }
 
