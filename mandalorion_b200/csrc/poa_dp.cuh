@@ -457,9 +457,12 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
         /* results of the window's rows, row w0+l in lane l: (beg_sn | end_sn<<16), (lpos+1 | rpos+1 << 16), tb offset */
         uint32_t d_a = 0, d_b = 0, d_tbo = 0;
         const int nrows = min(32, N - 1 - w0);
+        uint32_t ma_next = __reduce_or_sync(FULL, lane == 0 ? m_a : 0u);
         for (int l = 0; l < nrows; ++l) {
             const int i = w0 + l;
-            const uint32_t ma = __reduce_or_sync(FULL, lane == l ? m_a : 0u);
+            /* the metadata broadcast of row l+1 is issued a whole row ahead of its use */
+            const uint32_t ma = ma_next;
+            ma_next = __reduce_or_sync(FULL, lane == l + 1 ? m_a : 0u);
             const int nbase = ma & META_BASE;
             const int rem = (int)(ma >> 14);
             const bool simple = (ma & 32u) != 0;
