@@ -321,6 +321,7 @@ static SlotLayout make_layout(const Caps &c) {
     }
     L.remain = take(n * 4); L.meta = take(n * 4); L.rowinfo = take(n * 16); L.rowtb = take(n * 16);
     L.rowbest = take(n * 4); L.qmap = take(q * 4);
+    L.qprof = take(4ull * qprof_stride(c.qcap) * 4);
     L.pv = take(q * 4); L.pkey = take(q * 4); L.pnew = take(q * 4); L.psib = take(q * 4);
     L.nin = take(q * 4); L.nout = take(q * 4);
     L.cnt = take(n * 4); L.addin = take(n * 4); L.addout = take(n * 4); L.grow = take(n); L.srcof = take(n * 4);

@@ -58,6 +58,7 @@ struct SlotLayout {
     uint64_t tbcap;                                    // bytes of the traceback area
     uint64_t base[2], sib[2], creator[2], in_off[2], in_row[2], out_off[2], out_row[2], out_w[2];
     uint64_t remain, meta, rowinfo, rowtb, rowbest, qmap;
+    uint64_t qprof;                                    // query profile of the read being aligned: 4 bases x qprof_stride(qcap) words
     uint64_t pv, pkey, pnew, psib, nin, nout;          // per query position
     uint64_t cnt, addin, addout, grow, srcof;          // per row
     uint64_t tb;
@@ -90,6 +91,9 @@ struct KernelArgs {
     Packed16 K;
     int wcap;                        // cells per ring row
 };
+
+/* words between the base rows of the query profile (one word = the scores of two cells) */
+__host__ __device__ inline uint32_t qprof_stride(uint32_t qcap) { return ((qcap >> 1) + 24u) & ~7u; }
 
 enum StatIdx { SI_CELLS = 0, SI_INTOPS, SI_FULL, SI_ALN, SI_ALN16, SI_ALN32, SI_TB,
                SI_T_PREP, SI_T_DP, SI_T_TB, SI_T_MERGE, SI_T_CONS, SI_T_BUSY, SI_COUNT };

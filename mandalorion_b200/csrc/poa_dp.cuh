@@ -256,7 +256,7 @@ __host__ __device__ constexpr int ring16_row_words() { return 32 * WPL; }
 template <int WPL>
 __host__ __device__ constexpr int ring16_rows() { return WPL >= 4 ? 4 : 8; }   // rows kept in shared memory
 template <int WPL>
-__host__ __device__ constexpr int ring16_warp_words() { return ring16_rows<WPL>() * 3 * ring16_row_words<WPL>() + 5 * 32 * WPL + RING * 4; }
+__host__ __device__ constexpr int ring16_warp_words() { return ring16_rows<WPL>() * 3 * ring16_row_words<WPL>() + 5 * 32 * WPL + 32 * 5; }   // ring, profile, window records
 
 template <int WPL>
 __device__ __forceinline__ void ld_words(const uint32_t *p, uint32_t (&v)[WPL]) {
@@ -309,6 +309,14 @@ __device__ __forceinline__ int key_of(uint32_t h, uint32_t sel) {
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(h), "n"(T), "r"(sel));
     return (int)d;
 }
+/* the same key for the LOW half of h as one multiply-add: it runs on the FMA pipe, the packed DP
+ * keeps the ALU pipe busy */
+template <int T>
+__device__ __forceinline__ int key_lo(uint32_t h) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(d) : "r"(h), "n"(T));
+    return (int)d;
+}
 
 /*
  * Lane-stationary packed DP.  Column c of the query always lives in lane (c / CPL) mod 32, word
@@ -359,8 +367,23 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
     const uint32_t prof_a = smem_addr(ring + RINGV * 3 * RW + lane * WPL);     // + base * RW*4
     int4 *rowinfo_g = rowinfo_p(A, S);
     uint4 *rowtb_g = rowtb_p(A, S);
-    const uint32_t sel_lo = pin_reg(0x1054u), sel_hi = pin_reg(0x3254u);
+    const uint32_t sel_hi = pin_reg(0x3254u);
     const uint32_t lane_up = pack2(P.e1 * CPL * lane, P.e2 * CPL * lane);   // lane decays added back before the scan
+
+    /* query profile of the whole read, once: qprof[b][w] = (s(b, q[2w-1]), s(b, q[2w])), the scores
+     * of cells 2w and 2w+1 against node base b.  A lane that re-binds copies its words from here. */
+    uint32_t *qprof = qprof_p(A, S);
+    const int qps = (int)qprof_stride(A.L.qcap);
+    for (int wd = lane; wd <= (qlen >> 1); wd += 32) {
+        const int qa = q[max(2 * wd - 1, 0)], qc = q[min(2 * wd, qlen - 1)];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int sa = qa >= 4 ? 0 : (qa == b ? P.match : -P.mismatch);
+            const int sb = qc >= 4 ? 0 : (qc == b ? P.match : -P.mismatch);
+            qprof[b * qps + wd] = pack2(sa, sb);
+        }
+    }
+    __syncwarp();
 
     /* lane binding (changes only when the band does) */
     int cur_beg = -1, cur_hi = -1, cur_width = 0;
@@ -383,18 +406,15 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
         const int nc0 = beg + rl * CPL;
         if (nc0 != c0) {
             c0 = nc0;
-            int qb = q[min(max(c0 - 1, 0), qlen - 1)];
 #pragma unroll
-            for (int m = 0; m < WPL; ++m) {
-                Hp[m] = E1p[m] = E2p[m] = NEG2;
-                /* word m = cells c0+2m, c0+2m+1; cell j consumes q[j-1] */
-                const int qa = qb, qc = q[min(c0 + 2 * m, qlen - 1)];
-                qb = q[min(c0 + 2 * m + 1, qlen - 1)];
+            for (int m = 0; m < WPL; ++m) Hp[m] = E1p[m] = E2p[m] = NEG2;
+            if (c0 <= qlen) {                 // the lane's new columns: copy their profile words
+                const uint32_t *src = qprof + (c0 >> 1);
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
-                    const int sa = qa >= 4 ? 0 : (qa == b ? P.match : -P.mismatch);
-                    const int sb = qc >= 4 ? 0 : (qc == b ? P.match : -P.mismatch);
-                    sts_word(prof_a + (b * RW + m) * 4, pack2(sa, sb));
+                    uint32_t v[WPL];
+                    ld_words<WPL>(src + b * qps, v);
+                    sts_words<WPL>(prof_a + b * (RW * 4), v);
                 }
             }
         }
@@ -457,12 +477,9 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
         /* results of the window's rows, row w0+l in lane l: (beg_sn | end_sn<<16), (lpos+1 | rpos+1 << 16), tb offset */
         uint32_t d_a = 0, d_b = 0, d_tbo = 0;
         const int nrows = min(32, N - 1 - w0);
-        uint32_t ma_next = __reduce_or_sync(FULL, lane == 0 ? m_a : 0u);
         for (int l = 0; l < nrows; ++l) {
             const int i = w0 + l;
-            /* the metadata broadcast of row l+1 is issued a whole row ahead of its use */
-            const uint32_t ma = ma_next;
-            ma_next = __reduce_or_sync(FULL, lane == l + 1 ? m_a : 0u);
+            const uint32_t ma = __reduce_or_sync(FULL, lane == l ? m_a : 0u);   // uniform
             const int nbase = ma & META_BASE;
             const int rem = (int)(ma >> 14);
             const bool simple = (ma & 32u) != 0;
@@ -614,28 +631,28 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
              * key = H << 16 | column (resp. reversed column) relative to the band start */
             int kr, kl;
             {
-                int r0 = key_of<0>(Hp[0], sel_lo), r1 = key_of<1>(Hp[0], sel_hi);
-                int l0 = key_of<CPL - 1>(Hp[0], sel_lo), l1 = key_of<CPL - 2>(Hp[0], sel_hi);
+                int r0 = key_lo<0>(Hp[0]), r1 = key_of<1>(Hp[0], sel_hi);
+                int l0 = key_lo<CPL - 1>(Hp[0]), l1 = key_of<CPL - 2>(Hp[0], sel_hi);
                 kr = max(r0, r1); kl = max(l0, l1);
                 if constexpr (WPL >= 2) {
-                    kr = __vimax3_s32(kr, key_of<2>(Hp[1], sel_lo), key_of<3>(Hp[1], sel_hi));
-                    kl = __vimax3_s32(kl, key_of<CPL - 3>(Hp[1], sel_lo), key_of<CPL - 4>(Hp[1], sel_hi));
+                    kr = __vimax3_s32(kr, key_lo<2>(Hp[1]), key_of<3>(Hp[1], sel_hi));
+                    kl = __vimax3_s32(kl, key_lo<CPL - 3>(Hp[1]), key_of<CPL - 4>(Hp[1], sel_hi));
                 }
                 if constexpr (WPL >= 4) {
-                    kr = __vimax3_s32(kr, key_of<4>(Hp[2], sel_lo), key_of<5>(Hp[2], sel_hi));
-                    kl = __vimax3_s32(kl, key_of<CPL - 5>(Hp[2], sel_lo), key_of<CPL - 6>(Hp[2], sel_hi));
-                    kr = __vimax3_s32(kr, key_of<6>(Hp[3], sel_lo), key_of<7>(Hp[3], sel_hi));
-                    kl = __vimax3_s32(kl, key_of<CPL - 7>(Hp[3], sel_lo), key_of<CPL - 8>(Hp[3], sel_hi));
+                    kr = __vimax3_s32(kr, key_lo<4>(Hp[2]), key_of<5>(Hp[2], sel_hi));
+                    kl = __vimax3_s32(kl, key_lo<CPL - 5>(Hp[2]), key_of<CPL - 6>(Hp[2], sel_hi));
+                    kr = __vimax3_s32(kr, key_lo<6>(Hp[3]), key_of<7>(Hp[3], sel_hi));
+                    kl = __vimax3_s32(kl, key_lo<CPL - 7>(Hp[3]), key_of<CPL - 8>(Hp[3], sel_hi));
                 }
                 if constexpr (WPL >= 8) {
-                    kr = __vimax3_s32(kr, key_of<8>(Hp[4], sel_lo), key_of<9>(Hp[4], sel_hi));
-                    kl = __vimax3_s32(kl, key_of<CPL - 9>(Hp[4], sel_lo), key_of<CPL - 10>(Hp[4], sel_hi));
-                    kr = __vimax3_s32(kr, key_of<10>(Hp[5], sel_lo), key_of<11>(Hp[5], sel_hi));
-                    kl = __vimax3_s32(kl, key_of<CPL - 11>(Hp[5], sel_lo), key_of<CPL - 12>(Hp[5], sel_hi));
-                    kr = __vimax3_s32(kr, key_of<12>(Hp[6], sel_lo), key_of<13>(Hp[6], sel_hi));
-                    kl = __vimax3_s32(kl, key_of<CPL - 13>(Hp[6], sel_lo), key_of<CPL - 14>(Hp[6], sel_hi));
-                    kr = __vimax3_s32(kr, key_of<14>(Hp[7], sel_lo), key_of<15>(Hp[7], sel_hi));
-                    kl = __vimax3_s32(kl, key_of<CPL - 15>(Hp[7], sel_lo), key_of<CPL - 16>(Hp[7], sel_hi));
+                    kr = __vimax3_s32(kr, key_lo<8>(Hp[4]), key_of<9>(Hp[4], sel_hi));
+                    kl = __vimax3_s32(kl, key_lo<CPL - 9>(Hp[4]), key_of<CPL - 10>(Hp[4], sel_hi));
+                    kr = __vimax3_s32(kr, key_lo<10>(Hp[5]), key_of<11>(Hp[5], sel_hi));
+                    kl = __vimax3_s32(kl, key_lo<CPL - 11>(Hp[5]), key_of<CPL - 12>(Hp[5], sel_hi));
+                    kr = __vimax3_s32(kr, key_lo<12>(Hp[6]), key_of<13>(Hp[6], sel_hi));
+                    kl = __vimax3_s32(kl, key_lo<CPL - 13>(Hp[6]), key_of<CPL - 14>(Hp[6], sel_hi));
+                    kr = __vimax3_s32(kr, key_lo<14>(Hp[7]), key_of<15>(Hp[7], sel_hi));
+                    kl = __vimax3_s32(kl, key_lo<CPL - 15>(Hp[7]), key_of<CPL - 16>(Hp[7], sel_hi));
                 }
             }
             kr = __reduce_max_sync(FULL, kr + rl * CPL);

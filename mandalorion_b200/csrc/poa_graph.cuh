@@ -34,7 +34,7 @@ MPOA_ACC2(uint8_t, base) MPOA_ACC2(uint8_t, sib) MPOA_ACC2(int32_t, creator)
 MPOA_ACC2(uint32_t, in_off) MPOA_ACC2(uint32_t, in_row) MPOA_ACC2(uint32_t, out_off)
 MPOA_ACC2(uint32_t, out_row) MPOA_ACC2(int32_t, out_w)
 MPOA_ACC(int32_t, remain) MPOA_ACC(uint32_t, meta) MPOA_ACC(int4, rowinfo) MPOA_ACC(uint4, rowtb)
-MPOA_ACC(int32_t, rowbest) MPOA_ACC(int32_t, qmap)
+MPOA_ACC(int32_t, rowbest) MPOA_ACC(int32_t, qmap) MPOA_ACC(uint32_t, qprof)
 MPOA_ACC(int32_t, pv) MPOA_ACC(int32_t, pkey) MPOA_ACC(int32_t, pnew) MPOA_ACC(int32_t, psib)
 MPOA_ACC(int32_t, nin) MPOA_ACC(int32_t, nout)
 MPOA_ACC(int32_t, cnt) MPOA_ACC(int32_t, addin) MPOA_ACC(int32_t, addout) MPOA_ACC(int32_t, srcof)
