@@ -365,6 +365,7 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
     const uint32_t NEG2 = K.neg2;
     const uint32_t ring_a = smem_addr(ring + lane * WPL);                      // + (row & (RINGV-1)) * 3*RW*4 + array * RW*4
     const uint32_t prof_a = smem_addr(ring + RINGV * 3 * RW + lane * WPL);     // + base * RW*4
+    const uint32_t wrec_a = smem_addr(ring + RINGV * 3 * RW + 5 * RW);          // window records: 32 x {beg_sn, end_sn, lpos, rpos}, then 32 x tb offset
     int4 *rowinfo_g = rowinfo_p(A, S);
     uint4 *rowtb_g = rowtb_p(A, S);
     const uint32_t sel_hi = pin_reg(0x3254u);
@@ -474,8 +475,8 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                 m_a = (meta_p(A, S)[r] & 31u) | simple | ((uint32_t)min(npre, 255) << 6) | ((uint32_t)remain_p(A, S)[r] << 14);
             }
         }
-        /* results of the window's rows, row w0+l in lane l: (beg_sn | end_sn<<16), (lpos+1 | rpos+1 << 16), tb offset */
-        uint32_t d_a = 0, d_b = 0, d_tbo = 0;
+        /* the results of the window's rows (band vectors, row-maximum columns, traceback offset) are
+         * parked in shared memory by lane 0 and written to HBM by all lanes at the end of the window */
         const int nrows = min(32, N - 1 - w0);
         for (int l = 0; l < nrows; ++l) {
             const int i = w0 + l;
@@ -501,8 +502,9 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                     int bs, es, pl, pr;
                     if (p == i - 1) { bs = p_bs; es = p_es; pl = p_l; pr = p_r; }
                     else if (p >= w0) {
-                        const uint32_t a = __shfl_sync(FULL, d_a, p - w0), b = __shfl_sync(FULL, d_b, p - w0);
-                        bs = (int)(a & 0xffff); es = (int)(a >> 16); pl = (int)(b & 0xffff) - 1; pr = (int)(b >> 16) - 1;
+                        uint32_t v[4];
+                        lds_words<4>(wrec_a + (p - w0) * 16, v);
+                        bs = (int)v[0]; es = (int)v[1]; pl = (int)v[2]; pr = (int)v[3];
                     } else { const int4 pi = rowinfo_g[p]; bs = pi.x; es = pi.y; pl = pi.z; pr = pi.w; }
                     left = min(left, pl + 1);
                     right = max(right, pr + 1);
@@ -545,9 +547,10 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                     uint32_t ptbo = 0;
                     int pst = 0;              // words per array of the stored row
                     if (p >= w0) {
-                        const uint32_t a = __shfl_sync(FULL, d_a, p - w0);
-                        ptbo = __shfl_sync(FULL, d_tbo, p - w0);
-                        if (p == i - 1) { bs = p_bs; es = p_es; } else { bs = (int)(a & 0xffff); es = (int)(a >> 16); }
+                        uint32_t v[4];
+                        lds_words<4>(wrec_a + (p - w0) * 16, v);
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ptbo) : "r"(wrec_a + 512 + (p - w0) * 4));
+                        bs = (int)v[0]; es = (int)v[1];
                         pst = (int)stw_of(min(WCAP, max(0, min(((es + 1) << lg) - 1, qlen) - (bs << lg) + 1)));
                     } else if (p == i - 1) { bs = p_bs; es = p_es; }
                     else { const int4 pi = rowinfo_g[p]; bs = pi.x; es = pi.y; }
@@ -683,10 +686,10 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                 if ((kr >> 16) <= NEG16) { lpos = cur_beg; rpos = cur_beg + cur_width - 1; }   // nothing above -inf
             }
             p_bs = B.beg_sn; p_es = B.end_sn; p_l = lpos; p_r = rpos;
-            if (lane == l) {
-                d_a = (uint32_t)B.beg_sn | ((uint32_t)B.end_sn << 16);
-                d_b = (uint32_t)(lpos + 1) | ((uint32_t)(rpos + 1) << 16);
-                d_tbo = tbo;
+            if (lane == 0) {
+                const uint32_t v[4] = {(uint32_t)B.beg_sn, (uint32_t)B.end_sn, (uint32_t)lpos, (uint32_t)rpos};
+                sts_words<4>(wrec_a + l * 16, v);
+                sts_word(wrec_a + 512 + l * 4, tbo);
             }
             if (ma & META_TOSINK) {
                 /* H at the last cell of the row: the global best is picked among these after the DP */
@@ -699,10 +702,14 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
             }
         }
         /* the window's bookkeeping, one row per lane */
+        __syncwarp();
         if (lane < nrows) {
-            const int bs = (int)(d_a & 0xffff), es = (int)(d_a >> 16);
+            uint32_t v[4], d_tbo;
+            lds_words<4>(wrec_a + lane * 16, v);
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(d_tbo) : "r"(wrec_a + 512 + lane * 4));
+            const int bs = (int)v[0], es = (int)v[1];
             const int wd = min(WCAP, max(0, min(((es + 1) << lg) - 1, qlen) - (bs << lg) + 1));
-            rowinfo_g[w0 + lane] = make_int4(bs, es, (int)(d_b & 0xffff) - 1, (int)(d_b >> 16) - 1);
+            rowinfo_g[w0 + lane] = make_int4(bs, es, (int)v[2], (int)v[3]);
             rowtb_g[w0 + lane] = make_uint4(d_tbo, 2 * stw_of(wd), (uint32_t)m_p0, m_a & META_BASE);
         }
         __syncwarp();
