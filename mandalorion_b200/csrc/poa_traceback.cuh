@@ -40,6 +40,24 @@ __device__ __forceinline__ RowView<T> row_view(const KernelArgs &A, const Slot &
     return v;
 }
 
+/* row_view through the shared-memory window of the last speculative batch (slot x = row wb - x) */
+template <typename T>
+__device__ __forceinline__ RowView<T> row_view_w(const KernelArgs &A, const Slot &S, int r, int lg, int qlen, int wb,
+                                                 const int4 *winfo, const uint4 *wtb, int tbw) {
+    const int x = wb - r;
+    if ((unsigned)x >= (unsigned)tbw) return row_view<T>(A, S, r, lg, qlen);
+    RowView<T> v;
+    const int4 info = winfo[x];
+    const uint4 rt = wtb[x];
+    v.beg_sn = info.x; v.end_sn = info.y;
+    v.beg = info.x << lg;
+    v.end = ((info.y + 1) << lg) - 1;
+    v.hi = min(v.end, qlen);
+    v.stride = (int)rt.y;
+    v.h = reinterpret_cast<const T *>(reinterpret_cast<const uint32_t *>(tb_p(A, S)) + rt.x);
+    return v;
+}
+
 template <typename T>
 __device__ __forceinline__ int rv_get(const RowView<T> &v, int arr, int j) {
     return (j >= v.beg && j <= v.hi) ? (int)v.h[arr * v.stride + (j - v.beg)] : NEG;
@@ -105,8 +123,10 @@ __device__ __forceinline__ bool traceback(const KernelArgs &A, const Slot &S, co
     for (int t = j + lane; t < qlen; t += 32) qmap[t] = -1;
     int4 *winfo = reinterpret_cast<int4 *>(scratch);          // [TBW] rowinfo of rows i, i-1, ...
     uint4 *wtb = reinterpret_cast<uint4 *>(scratch) + TBW;    // [TBW] rowtb
+    int wb = INT_MIN / 2;        // row held by window slot 0 (none yet)
+    bool retry_batch = true;     // false right after a batch that stopped early: its next step is known to fail
     while (i > 0 && j > 0) {
-        if (cur_op == OP_ALL) {
+        if (cur_op == OP_ALL && retry_batch) {
             /*
              * Speculative batch: in state ALL the next step is "diagonal to the FIRST predecessor"
              * whenever H[p0][j-1] + s == H[i][j].  The chain i -> p0(i) -> p0(p0(i)) ... is followed
@@ -119,6 +139,7 @@ __device__ __forceinline__ bool traceback(const KernelArgs &A, const Slot &S, co
                 const int row = i - x;
                 if (row >= 0) { winfo[x] = rowinfo_p(A, S)[row]; wtb[x] = rowtb_p(A, S)[row]; }
             }
+            wb = i;
             __syncwarp();
             int x = 0, myx = lane == 0 ? 0 : -1;
             for (int l = 1; l < 32; ++l) {
@@ -144,6 +165,7 @@ __device__ __forceinline__ bool traceback(const KernelArgs &A, const Slot &S, co
             const bool nok = __shfl_down_sync(FULL, inband ? 1 : 0, 1) != 0;
             const bool ok = lane < 31 && inband && row > 0 && col >= 1 && nok && (hnext + s == hval);
             const int cnt = __ffs(~__ballot_sync(FULL, ok)) - 1;
+            retry_batch = cnt >= 31;
             if (cnt > 0) {
                 if (lane < cnt) qmap[col - 1] = row;
                 i = __shfl_sync(FULL, row, cnt);
@@ -151,46 +173,61 @@ __device__ __forceinline__ bool traceback(const KernelArgs &A, const Slot &S, co
                 continue;
             }
         }
-        const RowView<T> vi = row_view<T>(A, S, i, lg, qlen);
+        retry_batch = true;
+        const RowView<T> vi = row_view_w<T>(A, S, i, lg, qlen, wb, winfo, wtb, TBW);
         const int in0 = (int)in_off[i], npre = (int)in_off[i + 1] - in0;
         const int nbase = (int)(meta_p(A, S)[i] & META_BASE);
         const int s = score_of(P, nbase, q[j - 1]);
         const int hij = rv_get(vi, 0, j);
         bool hit = false;
+        /* The predecessors are probed by one lane each (32 at a time); the FIRST one in edge order
+         * that qualifies is taken, exactly like abPOA's loop over pre_id. */
         if (cur_op & OP_M) {
-            for (int k = 0; k < npre; ++k) {
-                const int p = (int)in_row[in0 + k];
-                const RowView<T> vp = row_view<T>(A, S, p, lg, qlen);
-                if (j - 1 < vp.beg || j - 1 > vp.end) continue;
-                if (rv_get(vp, 0, j - 1) + s == hij) {
+            for (int k0 = 0; k0 < npre && !hit; k0 += 32) {
+                const int k = k0 + lane;
+                int p = 0;
+                bool m = false;
+                if (k < npre) {
+                    p = (int)in_row[in0 + k];
+                    const RowView<T> vp = row_view_w<T>(A, S, p, lg, qlen, wb, winfo, wtb, TBW);
+                    if (j - 1 >= vp.beg && j - 1 <= vp.end) m = rv_get(vp, 0, j - 1) + s == hij;
+                }
+                const unsigned b = __ballot_sync(FULL, m);
+                if (b) {
                     if (lane == 0) qmap[j - 1] = i;
-                    i = p; --j; hit = true; cur_op = OP_ALL;
-                    break;
+                    i = __shfl_sync(FULL, p, __ffs(b) - 1);
+                    --j; hit = true; cur_op = OP_ALL;
                 }
             }
         }
         if (!hit && (cur_op & OP_E)) {
-            for (int k = 0; k < npre && !hit; ++k) {
-                const int p = (int)in_row[in0 + k];
-                const RowView<T> vp = row_view<T>(A, S, p, lg, qlen);
-                if (j < vp.beg || j > vp.end) continue;
-                if (cur_op & OP_E1) {
-                    const int pe1 = rv_get(vp, 1, j);
-                    const bool take = (cur_op & OP_M) ? (hij == pe1) : (rv_get(vi, 1, j) == pe1 - P.e1);
-                    if (take) {
-                        cur_op = (rv_get(vp, 0, j) - P.oe1 == pe1) ? (OP_M | OP_F) : OP_E1;
-                        i = p; hit = true;
-                        break;
+            const int e1ij = rv_get(vi, 1, j), e2ij = rv_get(vi, 2, j);
+            for (int k0 = 0; k0 < npre && !hit; k0 += 32) {
+                const int k = k0 + lane;
+                int p = 0, nop = 0;
+                if (k < npre) {
+                    p = (int)in_row[in0 + k];
+                    const RowView<T> vp = row_view_w<T>(A, S, p, lg, qlen, wb, winfo, wtb, TBW);
+                    if (j >= vp.beg && j <= vp.end) {
+                        const int hp = rv_get(vp, 0, j);
+                        if (cur_op & OP_E1) {
+                            const int pe1 = rv_get(vp, 1, j);
+                            const bool take = (cur_op & OP_M) ? (hij == pe1) : (e1ij == pe1 - P.e1);
+                            if (take) nop = (hp - P.oe1 == pe1) ? (OP_M | OP_F) : OP_E1;
+                        }
+                        if (nop == 0 && (cur_op & OP_E2)) {
+                            const int pe2 = rv_get(vp, 2, j);
+                            const bool take = (cur_op & OP_M) ? (hij == pe2) : (e2ij == pe2 - P.e2);
+                            if (take) nop = (hp - P.oe2 == pe2) ? (OP_M | OP_F) : OP_E2;
+                        }
                     }
                 }
-                if (cur_op & OP_E2) {
-                    const int pe2 = rv_get(vp, 2, j);
-                    const bool take = (cur_op & OP_M) ? (hij == pe2) : (rv_get(vi, 2, j) == pe2 - P.e2);
-                    if (take) {
-                        cur_op = (rv_get(vp, 0, j) - P.oe2 == pe2) ? (OP_M | OP_F) : OP_E2;
-                        i = p; hit = true;
-                        break;
-                    }
+                const unsigned b = __ballot_sync(FULL, nop != 0);
+                if (b) {
+                    const int sl = __ffs(b) - 1;
+                    i = __shfl_sync(FULL, p, sl);
+                    cur_op = __shfl_sync(FULL, nop, sl);
+                    hit = true;
                 }
             }
         }
