@@ -89,7 +89,7 @@ __device__ __forceinline__ void init_graph(const KernelArgs &A, const Slot &S, c
             const bool real = r >= 1 && r <= len;
             base_p(A, S)[r] = real ? seq[r - 1] : 0;
             sib_p(A, S)[r] = 0;
-            creator_p(A, S)[r] = real ? creator0 + r - 1 : -1;
+            if (A.tr_node) creator_p(A, S)[r] = real ? creator0 + r - 1 : -1;   // node identity: only the trace needs it
             if (r >= 1) in_row_p(A, S)[r - 1] = r - 1;
             if (r < N - 1) { out_row_p(A, S)[r] = r + 1; out_w_p(A, S)[r] = 1; }
         }
@@ -258,8 +258,20 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
                 carry += __shfl_sync(FULL, incl, 31);
             }
         }
-        for (int t = lane; t < qlen; t += 32)
-            if (pv[t] < 0) srcof[pkey[t] + 1 + pnew[t]] = -(t + 1);
+        for (int t0 = 0; t0 < qlen; t0 += 32 * MK) {
+            int pvv[MK], pk[MK], pn[MK];
+#pragma unroll
+            for (int u = 0; u < MK; ++u) {
+                const int t = t0 + u * 32 + lane;
+                pvv[u] = 0; pk[u] = 0; pn[u] = 0;
+                if (t < qlen) { pvv[u] = pv[t]; pk[u] = pkey[t]; pn[u] = pnew[t]; }
+            }
+#pragma unroll
+            for (int u = 0; u < MK; ++u) {
+                const int t = t0 + u * 32 + lane;
+                if (t < qlen && pvv[u] < 0) srcof[pk[u] + 1 + pn[u]] = -(t + 1);
+            }
+        }
     }
     __syncwarp();
 
@@ -349,7 +361,7 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
                         if (ao[u] >= 0) { n_out_row[oo] = ao[u]; n_out_w[oo++] = 1; }
                         n_base[nr] = base[sr];
                         n_sib[nr] = (uint8_t)(sib[sr] + grow[sr]);
-                        n_creator[nr] = creator[sr];
+                        if (tr_node) n_creator[nr] = creator[sr];
                     } else {
                         const int t = -sr - 1;
                         n_in_row[io] = nin[t];
@@ -360,7 +372,7 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
                         int sb = 0;
                         if (so >= 0) { const int o = sib[so]; sb = ((o >> 4) + (o & 15) + 1) << 4; }
                         n_sib[nr] = (uint8_t)sb;
-                        n_creator[nr] = creator0 + t;
+                        if (tr_node) n_creator[nr] = creator0 + t;
                     }
                 }
                 carry_in += __shfl_sync(FULL, iin, 31);
