@@ -167,13 +167,16 @@ __device__ __forceinline__ void remain_pass(const KernelArgs &A, const Slot &S, 
  */
 __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, int &par, int &N, int &E, const uint8_t *__restrict__ q,
                           int qlen, int creator0, int32_t *tr_aln, int32_t *tr_node, int lane) {
-    const uint8_t *base = base_p(A, S), *sib = sib_p(A, S);
-    const uint32_t *out_off = out_off_p(A, S), *out_row = out_row_p(A, S), *in_off = in_off_p(A, S), *in_row = in_row_p(A, S);
+    const uint8_t *__restrict__ base = base_p(A, S), *__restrict__ sib = sib_p(A, S);
+    const uint32_t *__restrict__ out_off = out_off_p(A, S), *__restrict__ out_row = out_row_p(A, S);
+    const uint32_t *__restrict__ in_off = in_off_p(A, S), *__restrict__ in_row = in_row_p(A, S);
     int32_t *out_w = out_w_p(A, S);
 
-    /* Every pass below handles MK*32 elements per iteration in two stages: first all the
-     * (independent) dependent-load chains of the MK sub-chunks, then the cross-lane scans and the
-     * stores -- so MK global-memory round trips overlap instead of being paid one after another. */
+    /* The passes are bound by memory latency, so every pass handles MK*32 elements per iteration and
+     * is written LEVEL BY LEVEL: all loads of one dependency level (for all MK sub-chunks) are issued
+     * before anything that depends on them, and no store sits between the levels.  The common case
+     * (at most two in- and out-edges per row, a base that matches its aligned node) is covered by the
+     * batched levels; the rest falls into short serial loops. */
     constexpr int MK = 4;
     int32_t *cnt = cnt_p(A, S), *addin = addin_p(A, S), *addout = addout_p(A, S), *srcof = srcof_p(A, S);
     int32_t *pv = pv_p(A, S), *pkey = pkey_p(A, S), *pnew = pnew_p(A, S), *psib = psib_p(A, S);
@@ -188,22 +191,34 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
     int carry_key = 0, carry_new = 0;
     for (int t0 = 0; t0 < qlen; t0 += 32 * MK) {
         int isnew[MK], v[MK], key[MK], sibof[MK];
+        int r_[MK], b_[MK], br_[MK], sr_[MK];
+#pragma unroll
+        for (int u = 0; u < MK; ++u) {        // level 1: the aligned row and the query base
+            const int t = t0 + u * 32 + lane;
+            r_[u] = -1; b_[u] = 0;
+            if (t < qlen) { r_[u] = qmap[t]; b_[u] = q[t]; }
+        }
+#pragma unroll
+        for (int u = 0; u < MK; ++u) {        // level 2: that row's base and sibling byte
+            br_[u] = 0; sr_[u] = 0;
+            if (r_[u] >= 0) { br_[u] = base[r_[u]]; sr_[u] = sib[r_[u]]; }
+        }
 #pragma unroll
         for (int u = 0; u < MK; ++u) {
             const int t = t0 + u * 32 + lane;
             isnew[u] = 0; v[u] = -1; key[u] = -1; sibof[u] = -1;
             if (t < qlen) {
-                const int r = qmap[t];
-                const int b = q[t];
+                const int r = r_[u];
+                const int b = b_[u];
                 if (r >= 0) {
-                    if (base[r] == b) v[u] = r;
-                    else {
-                        const int sb = sib[r], before = sb >> 4, after = sb & 15;
+                    if (br_[u] == b) { v[u] = r; key[u] = r + (sr_[u] & 15); }
+                    else {                    // rare: look for the base among the aligned siblings
+                        const int sb = sr_[u], before = sb >> 4, after = sb & 15;
                         for (int x = r - before; x <= r + after; ++x)
                             if (x != r && base[x] == b) v[u] = x;
                         if (v[u] < 0) { isnew[u] = 1; sibof[u] = r; key[u] = r + after; }
+                        else key[u] = v[u] + (sib[v[u]] & 15);
                     }
-                    if (!isnew[u]) key[u] = v[u] + (sib[v[u]] & 15);
                     if (tr_aln) tr_aln[t] = creator[r];
                 } else {
                     isnew[u] = 1;
@@ -278,31 +293,54 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
     /* U3: the path edges u[t-1] -> u[t], t = 0..qlen (u[-1] = source, u[qlen] = sink) */
     int n_new_edges = 0;
     for (int t0 = 0; t0 <= qlen; t0 += 32 * MK) {
-        int from_old[MK], to_old[MK], from_new[MK], to_new[MK];
+        int from_old[MK], to_old[MK], km[MK], nm[MK], kt[MK], nt[MK];
+        int cf[MK], ct[MK], e0[MK], w0[MK];
         uint32_t o0[MK], o1[MK];
 #pragma unroll
-        for (int u = 0; u < MK; ++u) {
+        for (int u = 0; u < MK; ++u) {        // level 1: the two path nodes of the edge
             const int t = t0 + u * 32 + lane;
-            from_old[u] = to_old[u] = -2; o0[u] = o1[u] = 0; from_new[u] = to_new[u] = 0;
+            from_old[u] = to_old[u] = -2; km[u] = nm[u] = kt[u] = nt[u] = 0;
             if (t <= qlen) {
-                from_old[u] = t == 0 ? 0 : pv[t - 1];
-                to_old[u] = t == qlen ? N - 1 : pv[t];
-                from_new[u] = from_old[u] >= 0 ? from_old[u] + cnt[from_old[u]] : pkey[t - 1] + 1 + pnew[t - 1];
-                to_new[u] = to_old[u] >= 0 ? to_old[u] + cnt[to_old[u]] : pkey[t] + 1 + pnew[t];
-                if (from_old[u] >= 0 && to_old[u] >= 0) { o0[u] = out_off[from_old[u]]; o1[u] = out_off[from_old[u] + 1]; }
+                from_old[u] = 0; to_old[u] = N - 1;
+                if (t > 0) { from_old[u] = pv[t - 1]; km[u] = pkey[t - 1]; nm[u] = pnew[t - 1]; }
+                if (t < qlen) { to_old[u] = pv[t]; kt[u] = pkey[t]; nt[u] = pnew[t]; }
             }
+        }
+#pragma unroll
+        for (int u = 0; u < MK; ++u) {        // level 2: their shifts, the out-edge list of the source node
+            cf[u] = ct[u] = 0; o0[u] = o1[u] = 0;
+            if (from_old[u] >= 0) cf[u] = cnt[from_old[u]];
+            if (to_old[u] >= 0) ct[u] = cnt[to_old[u]];
+            if (from_old[u] >= 0 && to_old[u] >= 0) { o0[u] = out_off[from_old[u]]; o1[u] = out_off[from_old[u] + 1]; }
+        }
+#pragma unroll
+        for (int u = 0; u < MK; ++u) {        // level 3: the first out-edge
+            e0[u] = -1;
+            if (o1[u] > o0[u]) e0[u] = (int)out_row[o0[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < MK; ++u) {        // level 4: its weight when it is the path edge
+            w0[u] = 0;
+            if (o1[u] > o0[u] && e0[u] == to_old[u]) w0[u] = out_w[o0[u]];
         }
 #pragma unroll
         for (int u = 0; u < MK; ++u) {
             const int t = t0 + u * 32 + lane;
             if (t <= qlen) {
+                const int from_new = from_old[u] >= 0 ? from_old[u] + cf[u] : km[u] + 1 + nm[u];
+                const int to_new = to_old[u] >= 0 ? to_old[u] + ct[u] : kt[u] + 1 + nt[u];
                 bool found = false;
-                for (uint32_t e = o0[u]; e < o1[u]; ++e)
-                    if ((int)out_row[e] == to_old[u]) { out_w[e] += 1; found = true; break; }
+                if (o1[u] > o0[u]) {
+                    if (e0[u] == to_old[u]) { out_w[o0[u]] = w0[u] + 1; found = true; }
+                    else {
+                        for (uint32_t e = o0[u] + 1; e < o1[u]; ++e)
+                            if ((int)out_row[e] == to_old[u]) { out_w[e] += 1; found = true; break; }
+                    }
+                }
                 if (!found) {
                     ++n_new_edges;
-                    if (from_old[u] >= 0) addout[from_old[u]] = to_new[u]; else nout[t - 1] = to_new[u];
-                    if (to_old[u] >= 0) addin[to_old[u]] = from_new[u]; else nin[t] = from_new[u];
+                    if (from_old[u] >= 0) addout[from_old[u]] = to_new; else nout[t - 1] = to_new;
+                    if (to_old[u] >= 0) addin[to_old[u]] = from_new; else nin[t] = from_new;
                 }
             }
         }
@@ -321,25 +359,62 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
         int32_t *n_out_w = n_out_w_p(A, S), *n_creator = n_creator_p(A, S);
         uint8_t *n_base = n_base_p(A, S), *n_sib = n_sib_p(A, S);
         for (int r0 = 0; r0 < N2; r0 += 32 * MK) {
-            int din[MK], dout[MK], src[MK], ai[MK], ao[MK];
+            int din[MK], dout[MK], src[MK], ai[MK], ao[MK], nin_old[MK], nout_old[MK];
             uint32_t i0[MK], o0[MK];
+            int xa[MK], xb[MK], ya[MK], yb[MK], wa[MK], wb[MK];      // first two in- / out-edges (+ weights)
+            int nb[MK], sbv[MK], gr[MK], cre[MK];                     // base, sibling byte (+ growth), creator
+            int so[MK];
 #pragma unroll
-            for (int u = 0; u < MK; ++u) {
+            for (int u = 0; u < MK; ++u) {    // level 1: which old row (or which new node) lands here
                 const int nr = r0 + u * 32 + lane;
-                din[u] = dout[u] = 0; src[u] = 0; ai[u] = ao[u] = -1; i0[u] = o0[u] = 0;
+                src[u] = 0;
+                if (nr < N2) src[u] = srcof[nr];
+            }
+#pragma unroll
+            for (int u = 0; u < MK; ++u) {    // level 2: its edge lists, added edges, node bytes
+                const int nr = r0 + u * 32 + lane;
+                din[u] = dout[u] = 0; ai[u] = ao[u] = -1; i0[u] = o0[u] = 0; nin_old[u] = nout_old[u] = 0;
+                nb[u] = sbv[u] = gr[u] = 0; cre[u] = 0; so[u] = -1;
+                xa[u] = xb[u] = ya[u] = yb[u] = 0; wa[u] = wb[u] = 0;
                 if (nr < N2) {
-                    src[u] = srcof[nr];
-                    if (src[u] >= 0) {
-                        i0[u] = in_off[src[u]]; o0[u] = out_off[src[u]];
-                        ai[u] = addin[src[u]]; ao[u] = addout[src[u]];
-                        din[u] = (int)(in_off[src[u] + 1] - i0[u]) + (ai[u] >= 0);
-                        dout[u] = (int)(out_off[src[u] + 1] - o0[u]) + (ao[u] >= 0);
-                    } else din[u] = dout[u] = 1;
+                    const int sr = src[u];
+                    if (sr >= 0) {
+                        i0[u] = in_off[sr]; o0[u] = out_off[sr];
+                        nin_old[u] = (int)(in_off[sr + 1] - i0[u]); nout_old[u] = (int)(out_off[sr + 1] - o0[u]);
+                        ai[u] = addin[sr]; ao[u] = addout[sr];
+                        nb[u] = base[sr]; sbv[u] = sib[sr]; gr[u] = grow[sr];
+                        if (tr_node) cre[u] = creator[sr];
+                    } else {
+                        const int t = -sr - 1;
+                        xa[u] = nin[t]; ya[u] = nout[t]; nb[u] = q[t]; so[u] = psib[t];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < MK; ++u) {    // level 3: the first two old edges on each side
+                if (src[u] >= 0) {
+                    if (nin_old[u] > 0) xa[u] = (int)in_row[i0[u]];
+                    if (nin_old[u] > 1) xb[u] = (int)in_row[i0[u] + 1];
+                    if (nout_old[u] > 0) { ya[u] = (int)out_row[o0[u]]; wa[u] = out_w[o0[u]]; }
+                    if (nout_old[u] > 1) { yb[u] = (int)out_row[o0[u] + 1]; wb[u] = out_w[o0[u] + 1]; }
+                } else if (so[u] >= 0) sbv[u] = sib[so[u]];
+            }
+#pragma unroll
+            for (int u = 0; u < MK; ++u) {    // level 4: the shifts of their end points
+                if (src[u] >= 0) {
+                    if (nin_old[u] > 0) xa[u] += cnt[xa[u]];
+                    if (nin_old[u] > 1) xb[u] += cnt[xb[u]];
+                    if (nout_old[u] > 0) ya[u] += cnt[ya[u]];
+                    if (nout_old[u] > 1) yb[u] += cnt[yb[u]];
                 }
             }
 #pragma unroll
             for (int u = 0; u < MK; ++u) {
                 const int nr = r0 + u * 32 + lane;
+                if (nr < N2) {
+                    if (src[u] >= 0) { din[u] = nin_old[u] + (ai[u] >= 0); dout[u] = nout_old[u] + (ao[u] >= 0); }
+                    else din[u] = dout[u] = 1;
+                }
                 const int iin = warp_incl_sum(din[u], lane), iout = warp_incl_sum(dout[u], lane);
                 if (nr < N2) {
                     uint32_t io = carry_in + iin - din[u], oo = carry_out + iout - dout[u];
@@ -347,30 +422,32 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
                     n_out_off[nr] = oo;
                     const int sr = src[u];
                     if (sr >= 0) {
-                        const int nin_old = din[u] - (ai[u] >= 0), nout_old = dout[u] - (ao[u] >= 0);
-                        for (int e = 0; e < nin_old; ++e) {
+                        if (nin_old[u] > 0) n_in_row[io++] = xa[u];
+                        if (nin_old[u] > 1) n_in_row[io++] = xb[u];
+                        for (int e = 2; e < nin_old[u]; ++e) {
                             const int x = (int)in_row[i0[u] + e];
                             n_in_row[io++] = x + cnt[x];
                         }
                         if (ai[u] >= 0) n_in_row[io++] = ai[u];
-                        for (int e = 0; e < nout_old; ++e) {
+                        if (nout_old[u] > 0) { n_out_row[oo] = ya[u]; n_out_w[oo++] = wa[u]; }
+                        if (nout_old[u] > 1) { n_out_row[oo] = yb[u]; n_out_w[oo++] = wb[u]; }
+                        for (int e = 2; e < nout_old[u]; ++e) {
                             const int y = (int)out_row[o0[u] + e];
                             n_out_row[oo] = y + cnt[y];
                             n_out_w[oo++] = out_w[o0[u] + e];
                         }
                         if (ao[u] >= 0) { n_out_row[oo] = ao[u]; n_out_w[oo++] = 1; }
-                        n_base[nr] = base[sr];
-                        n_sib[nr] = (uint8_t)(sib[sr] + grow[sr]);
-                        if (tr_node) n_creator[nr] = creator[sr];
+                        n_base[nr] = (uint8_t)nb[u];
+                        n_sib[nr] = (uint8_t)(sbv[u] + gr[u]);
+                        if (tr_node) n_creator[nr] = cre[u];
                     } else {
                         const int t = -sr - 1;
-                        n_in_row[io] = nin[t];
-                        n_out_row[oo] = nout[t];
+                        n_in_row[io] = xa[u];
+                        n_out_row[oo] = ya[u];
                         n_out_w[oo] = 1;
-                        n_base[nr] = q[t];
-                        const int so = psib[t];
+                        n_base[nr] = (uint8_t)nb[u];
                         int sb = 0;
-                        if (so >= 0) { const int o = sib[so]; sb = ((o >> 4) + (o & 15) + 1) << 4; }
+                        if (so[u] >= 0) { const int o = sbv[u]; sb = ((o >> 4) + (o & 15) + 1) << 4; }
                         n_sib[nr] = (uint8_t)sb;
                         if (tr_node) n_creator[nr] = creator0 + t;
                     }
