@@ -177,7 +177,7 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
      * before anything that depends on them, and no store sits between the levels.  The common case
      * (at most two in- and out-edges per row, a base that matches its aligned node) is covered by the
      * batched levels; the rest falls into short serial loops. */
-    constexpr int MK = 4;
+    constexpr int MK = 2;
     int32_t *cnt = cnt_p(A, S), *addin = addin_p(A, S), *addout = addout_p(A, S), *srcof = srcof_p(A, S);
     int32_t *pv = pv_p(A, S), *pkey = pkey_p(A, S), *pnew = pnew_p(A, S), *psib = psib_p(A, S);
     int32_t *nin = nin_p(A, S), *nout = nout_p(A, S);
