@@ -123,6 +123,7 @@ __device__ __forceinline__ bool traceback(const KernelArgs &A, const Slot &S, co
     for (int t = j + lane; t < qlen; t += 32) qmap[t] = -1;
     int4 *winfo = reinterpret_cast<int4 *>(scratch);          // [TBW] rowinfo of rows i, i-1, ...
     uint4 *wtb = reinterpret_cast<uint4 *>(scratch) + TBW;    // [TBW] rowtb
+    int *jump = scratch + TBW * 8;                            // [5][TBW + 1] chain jump tables
     int wb = INT_MIN / 2;        // row held by window slot 0 (none yet)
     bool retry_batch = true;     // false right after a batch that stopped early: its next step is known to fail
     while (i > 0 && j > 0) {
@@ -137,18 +138,30 @@ __device__ __forceinline__ bool traceback(const KernelArgs &A, const Slot &S, co
             __syncwarp();
             for (int x = lane; x < TBW; x += 32) {
                 const int row = i - x;
-                if (row >= 0) { winfo[x] = rowinfo_p(A, S)[row]; wtb[x] = rowtb_p(A, S)[row]; }
+                int nx = TBW;                 // slot of the row's first predecessor (TBW: outside the window)
+                if (row >= 0) {
+                    const uint4 rt = rowtb_p(A, S)[row];
+                    winfo[x] = rowinfo_p(A, S)[row]; wtb[x] = rt;
+                    if (row > 0) nx = min(TBW, i - (int)rt.z);
+                }
+                jump[x] = nx;
             }
+            if (lane < 5) jump[lane * (TBW + 1) + TBW] = TBW;
             wb = i;
             __syncwarp();
-            int x = 0, myx = lane == 0 ? 0 : -1;
-            for (int l = 1; l < 32; ++l) {
-                const int row = i - x;
-                const int nx = row > 0 ? i - (int)wtb[x].z : TBW;
-                if (nx >= TBW) break;
-                x = nx;
-                if (lane == l) myx = x;
+            /* slot reached after l steps of the chain, for all l at once: pointer doubling
+             * (jump[k][x] = slot 2^k steps after x), then lane l composes the jumps of its bits */
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int *jk = jump + k * (TBW + 1);
+                for (int x = lane; x < TBW; x += 32) jump[(k + 1) * (TBW + 1) + x] = jk[jk[x]];
+                __syncwarp();
             }
+            int myx = 0;
+#pragma unroll
+            for (int k = 0; k < 5; ++k)
+                if ((lane >> k) & 1) myx = jump[k * (TBW + 1) + myx];
+            if (myx >= TBW) myx = -1;
             const int col = j - lane;
             bool inband = false;
             int hval = NEG, row = -1, s = 0;
