@@ -16,7 +16,7 @@
 
 namespace mpoa {
 
-constexpr int TBW = 64;   // rows looked at by one speculative traceback batch
+constexpr int TBW = 128;  // rows held by the traceback window (descriptors + chain jump tables); a batch needs 64 of them
 
 enum TbOps { OP_M = 1, OP_E1 = 2, OP_E2 = 4, OP_E = 6, OP_F1 = 8, OP_F2 = 16, OP_F = 24, OP_ALL = 31 };
 
@@ -135,29 +135,34 @@ __device__ __forceinline__ bool traceback(const KernelArgs &A, const Slot &S, co
              * prefix of successful checks is taken at once.  Every step taken is exactly the step
              * the serial logic below would have taken; a batch of length 0 falls through to it.
              */
-            __syncwarp();
-            for (int x = lane; x < TBW; x += 32) {
-                const int row = i - x;
-                int nx = TBW;                 // slot of the row's first predecessor (TBW: outside the window)
-                if (row >= 0) {
-                    const uint4 rt = rowtb_p(A, S)[row];
-                    winfo[x] = rowinfo_p(A, S)[row]; wtb[x] = rt;
-                    if (row > 0) nx = min(TBW, i - (int)rt.z);
-                }
-                jump[x] = nx;
-            }
-            if (lane < 5) jump[lane * (TBW + 1) + TBW] = TBW;
-            wb = i;
-            __syncwarp();
-            /* slot reached after l steps of the chain, for all l at once: pointer doubling
-             * (jump[k][x] = slot 2^k steps after x), then lane l composes the jumps of its bits */
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int *jk = jump + k * (TBW + 1);
-                for (int x = lane; x < TBW; x += 32) jump[(k + 1) * (TBW + 1) + x] = jk[jk[x]];
+            if ((unsigned)(wb - i) > (unsigned)(TBW - 64)) {
+                /* (re)load the window at row i: descriptors of rows i .. i-TBW+1 and, for every slot,
+                 * the slot of the row's first predecessor; then the jump tables by pointer doubling
+                 * (jump[k][x] = slot 2^k chain steps after x).  Batches starting in the upper half of
+                 * the window reuse all of it. */
                 __syncwarp();
+                for (int x = lane; x < TBW; x += 32) {
+                    const int row = i - x;
+                    int nx = TBW;             // TBW: outside the window / no predecessor
+                    if (row >= 0) {
+                        const uint4 rt = rowtb_p(A, S)[row];
+                        winfo[x] = rowinfo_p(A, S)[row]; wtb[x] = rt;
+                        if (row > 0) nx = min(TBW, i - (int)rt.z);
+                    }
+                    jump[x] = nx;
+                }
+                if (lane < 5) jump[lane * (TBW + 1) + TBW] = TBW;
+                wb = i;
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int *jk = jump + k * (TBW + 1);
+                    for (int x = lane; x < TBW; x += 32) jump[(k + 1) * (TBW + 1) + x] = jk[jk[x]];
+                    __syncwarp();
+                }
             }
-            int myx = 0;
+            /* slot reached after l chain steps from row i: lane l composes the jumps of its bits */
+            int myx = wb - i;
 #pragma unroll
             for (int k = 0; k < 5; ++k)
                 if ((lane >> k) & 1) myx = jump[k * (TBW + 1) + myx];
@@ -166,7 +171,7 @@ __device__ __forceinline__ bool traceback(const KernelArgs &A, const Slot &S, co
             bool inband = false;
             int hval = NEG, row = -1, s = 0;
             if (myx >= 0 && col >= 0) {
-                row = i - myx;
+                row = wb - myx;
                 const int4 info = winfo[myx];
                 const uint4 rt = wtb[myx];
                 const int beg = info.x << lg, hi = min(((info.y + 1) << lg) - 1, qlen);
