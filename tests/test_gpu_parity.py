@@ -101,6 +101,40 @@ def test_unrelated_reads_stress_band_edges(gpu_ctx):
     both(gpu_ctx, rag)
 
 
+def _with_long_indels(rng, template, n_events):
+    """a read of `template` with a few LONG insertions / deletions (20-150 nt) and sparse point errors"""
+    seq = list(template)
+    for _ in range(n_events):
+        pos = int(rng.integers(0, max(1, len(seq) - 1)))
+        ln = int(rng.integers(20, 150))
+        if rng.random() < 0.5:
+            seq[pos:pos] = list(random_seq(rng, ln))
+        else:
+            del seq[pos:pos + ln]
+    for k in range(len(seq)):
+        if rng.random() < 0.01:
+            seq[k] = "ACGT"[int(rng.integers(0, 4))]
+    return "".join(seq) or "A"
+
+
+def test_long_indels_cross_lanes(gpu_ctx):
+    # insertions longer than a lane's cells make the insertion recurrence (the rotated max-scan of
+    # the lane totals) carry over several lanes; long deletions make the band jump by whole vectors
+    rng = np.random.default_rng(11)
+    groups = []
+    for g in range(48):
+        t = random_seq(rng, int(rng.integers(300, 1800)))
+        groups.append([_with_long_indels(rng, t, int(rng.integers(0, 4))) for _ in range(int(rng.integers(3, 9)))])
+    both(gpu_ctx, groups)
+    # the same with a narrow and a wide fixed band (128-cell and 512-cell kernels)
+    for pk in (dict(wb=4, wf=0.0), dict(wb=150, wf=0.0)):
+        packed = pack_groups(groups[:16])
+        want = oracle_consensus_batch(packed=packed, trace=True, params=OracleParams(**pk), n_threads=os.cpu_count() or 1)
+        with PoaContext(0, PoaParams(**pk)) as ctx:
+            got = ctx.consensus_batch(packed=packed, trace=True)
+        assert_same(got, want, packed)
+
+
 @pytest.mark.parametrize("pk", [dict(simd_pn_i16=8, simd_pn_i32=4), dict(simd_pn_i16=32, simd_pn_i32=16),
                                 dict(wb=4, wf=0.0), dict(match=2, mismatch=4), dict(wb=40),
                                 dict(wb=120),                       # band 257..512 cells: the 16-cells-per-lane variant
