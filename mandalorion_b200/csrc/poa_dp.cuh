@@ -597,10 +597,19 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                 X[2 * m] = __byte_perm(a1, a2, 0x5410);
                 X[2 * m + 1] = __byte_perm(a1, a2, 0x7632);
             }
+            /* what the lane's own cells hand to the first cell of every 4-cell segment (FL) and to the
+             * next lane (T), without a carry-in: per segment a depth-2 tree instead of a serial chain,
+             *   S(X0..X3) = max(max(X3, X2-e), max(X1, X0-e) - 2e) */
             FL[0] = NEG2;
+            uint32_t T = NEG2;
 #pragma unroll
-            for (int t = 1; t < CPL; ++t) FL[t] = __viaddmax_s16x2(FL[t - 1], K.nee, X[t - 1]);
-            uint32_t T = __viaddmax_s16x2(FL[CPL - 1], K.nee, X[CPL - 1]);
+            for (int g = 0; g < CPL; g += SEG) {
+                const uint32_t u = __viaddmax_s16x2(X[g + 2], K.nee, X[g + 3]);
+                const uint32_t v = __viaddmax_s16x2(X[g], K.nee, X[g + 1]);
+                const uint32_t sg = __viaddmax_s16x2(v, K.tdec[2], u);
+                T = g == 0 ? sg : __viaddmax_s16x2(T, K.tdec[SEG], sg);
+                if (g + SEG < CPL) FL[g + SEG] = T;
+            }
             /* max-scan over the ROTATED lane order.  With lane * decay added back the decayed scan is
              * a plain running maximum; C = what reaches this lane's first cell from the lanes before */
             T = __vadd2(__shfl_sync(FULL, T, lane + lane - rl), lane_up);
