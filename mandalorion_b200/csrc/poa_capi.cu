@@ -378,13 +378,10 @@ static void fill_args(mpoa_ctx *ctx, const Launch &ln, int k, KernelArgs &A) {  
     A.P.wb = p.wb; A.P.wf = p.wf; A.P.pn16 = p.simd_pn_i16; A.P.pn32 = p.simd_pn_i32;
     A.wcap = ln.c.wcap;
     auto p2 = [](int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); };
-    const int cpl = 2 * std::max(1, ln.c.variant);
     A.K.neg2 = p2(NEG16, NEG16);
-    A.K.noe = p2(-A.P.oe1, -A.P.oe2); A.K.nee = p2(-A.P.e1, -A.P.e2);
+    A.K.nee = p2(-A.P.e1, -A.P.e2);
     A.K.noe1 = p2(-A.P.oe1, -A.P.oe1); A.K.noe2 = p2(-A.P.oe2, -A.P.oe2);
     A.K.ne1 = p2(-A.P.e1, -A.P.e1); A.K.ne2 = p2(-A.P.e2, -A.P.e2);
-    A.K.match2 = p2(A.P.match, A.P.match); A.K.mism2 = p2(-A.P.mismatch, -A.P.mismatch);
-    for (int d = 0; d < 5; ++d) A.K.dec[d] = p2(-A.P.e1 * cpl * (1 << d), -A.P.e2 * cpl * (1 << d));
     for (int t = 0; t < 16; ++t) A.K.tdec[t] = p2(-A.P.e1 * t, -A.P.e2 * t);
 }
 

@@ -30,7 +30,6 @@ constexpr int NEG = -(1 << 28);      // -inf surrogate in int32 arithmetic
 constexpr int NEG16 = -30000;        // -inf surrogate / floor of the packed int16 path
 constexpr int RING = 8;              // rows kept in the shared-memory ring
 constexpr int WARPS_PER_BLOCK = 4;
-constexpr int RING_PAD = 4;          // words of padding on each side of a packed ring row
 
 enum GroupStatus : int { ST_OK = 0, ST_EMPTY = 1, ST_RETRY = 2, ST_PENDING = 3, ST_RETRY_WIDE = 4, ST_RETRY_32 = 5 };
 
@@ -44,11 +43,9 @@ struct DevParams {
  * are used directly as instruction operands).  (a,b) = a in the low half, b in the high half. */
 struct Packed16 {
     uint32_t neg2;             // (NEG16, NEG16)
-    uint32_t noe, nee;         // (-oe1,-oe2), (-e1,-e2): per-cell words holding (F1,F2)
+    uint32_t nee;              // (-e1,-e2): per-cell words holding (F1,F2)
     uint32_t noe1, noe2;       // (-oe1,-oe1), (-oe2,-oe2): per-word of two cells
     uint32_t ne1, ne2;         // (-e1,-e1), (-e2,-e2)
-    uint32_t match2, mism2;    // (match,match), (-mismatch,-mismatch)
-    uint32_t dec[5];           // decay of the cross-lane F scan at distance 1,2,4,8,16 lanes
     uint32_t tdec[16];         // t * (-e1,-e2): decay inside a lane at cell t
 };
 

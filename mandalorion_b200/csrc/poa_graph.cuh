@@ -75,7 +75,7 @@ __device__ __forceinline__ int warp_scan_decay(int v, int e, int lane) {
     return v;
 }
 
-enum MetaBits { META_BASE = 7, META_FAR = 8, META_TOSINK = 16 };
+enum MetaBits { META_BASE = 7, META_TOSINK = 16 };
 
 /* ------------------------------------------------------------------------------------------ */
 /* graph: first read, remain pass                                                              */
@@ -115,14 +115,13 @@ __device__ __forceinline__ void remain_pass(const KernelArgs &A, const Slot &S, 
     for (int w0 = ((N - 2) / 32) * 32; w0 >= 0; w0 -= 32) {
         const int r = w0 + lane;
         const bool active = r <= N - 2;
-        int hs = N - 1, maxrow = 0, tosink = 0;
+        int hs = N - 1, tosink = 0;
         if (active) {
             const uint32_t o0 = out_off[r], o1 = out_off[r + 1];
             int maxw = -1;
             for (uint32_t e = o0; e < o1; ++e) {
                 const int t = (int)out_row[e], w = out_w[e];
                 if (w > maxw) { maxw = w; hs = t; }
-                maxrow = max(maxrow, t);
                 tosink |= (t == N - 1);
             }
         }
@@ -143,7 +142,7 @@ __device__ __forceinline__ void remain_pass(const KernelArgs &A, const Slot &S, 
         }
         if (active) {
             remain_p(A, S)[r] = acc;
-            meta_p(A, S)[r] = (uint32_t)base_p(A, S)[r] | ((maxrow - r >= RING) ? META_FAR : 0) | (tosink ? META_TOSINK : 0);
+            meta_p(A, S)[r] = (uint32_t)base_p(A, S)[r] | (tosink ? META_TOSINK : 0);
         }
         prev_vals = acc;
         __syncwarp();
