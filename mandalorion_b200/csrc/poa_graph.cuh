@@ -82,6 +82,7 @@ enum MetaBits { META_BASE = 7, META_TOSINK = 16 };
 /* ------------------------------------------------------------------------------------------ */
 
 /* first read = linear chain src -> b0 -> ... -> sink, every edge weight 1 */
+template <bool TRACE>
 __device__ __forceinline__ void init_graph(const KernelArgs &A, const Slot &S, const uint8_t *seq, int len, int creator0, int lane) {
     const int N = len + 2;
     for (int r = lane; r <= N; r += 32) {
@@ -89,7 +90,7 @@ __device__ __forceinline__ void init_graph(const KernelArgs &A, const Slot &S, c
             const bool real = r >= 1 && r <= len;
             base_p(A, S)[r] = real ? seq[r - 1] : 0;
             sib_p(A, S)[r] = 0;
-            if (A.tr_node) creator_p(A, S)[r] = real ? creator0 + r - 1 : -1;   // node identity: only the trace needs it
+            if constexpr (TRACE) creator_p(A, S)[r] = real ? creator0 + r - 1 : -1;   // node identity: only the trace needs it
             if (r >= 1) in_row_p(A, S)[r - 1] = r - 1;
             if (r < N - 1) { out_row_p(A, S)[r] = r + 1; out_w_p(A, S)[r] = 1; }
         }

@@ -62,7 +62,10 @@ __global__ void encode_bases_kernel(const uint8_t *__restrict__ ascii, uint8_t *
 /* the persistent kernel                                                                       */
 /* ------------------------------------------------------------------------------------------ */
 
-template <int V>
+/* TRACE: the per-read / per-base trace outputs of the ABI (parity tests).  It is a compile-time
+ * switch because the kernel's instruction footprint matters: the production instantiation is
+ * ~370 SASS instructions smaller and measurably faster (resident warps share the instruction cache). */
+template <int V, bool TRACE>
 __device__ __forceinline__ int process_group(const KernelArgs &A, int slot, int g, int *ring, int4 *ring_info, int lane,
                                              unsigned long long *st /* per-warp counters in shared memory, lane 0 only */) {
     const int64_t r0 = A.group_read_off[g], r1 = A.group_read_off[g + 1];
@@ -75,21 +78,18 @@ __device__ __forceinline__ int process_group(const KernelArgs &A, int slot, int 
         const int len = (int)(b1 - b0);
         const uint8_t *seq = A.codes + b0;
         const int creator0 = (int)(b0 - gbase);
-        int32_t *tr_aln = A.tr_aln ? A.tr_aln + b0 : nullptr;
-        int32_t *tr_node = A.tr_node ? A.tr_node + b0 : nullptr;
-        if (lane == 0) {
-            if (A.tr_score) A.tr_score[r] = 0;
-            if (A.tr_bits) A.tr_bits[r] = 0;
-            if (A.tr_cells) A.tr_cells[r] = 0;
+        int32_t *tr_aln = nullptr, *tr_node = nullptr;
+        if constexpr (TRACE) { tr_aln = A.tr_aln + b0; tr_node = A.tr_node + b0; }
+        if constexpr (TRACE) {
+            if (lane == 0) { A.tr_score[r] = 0; A.tr_bits[r] = 0; A.tr_cells[r] = 0; }
         }
         if (N == 0) {
             if (len <= 0) return ST_EMPTY;
             if ((uint32_t)(len + 2) > A.L.ncap || (uint32_t)(len + 1) > A.L.ecap) return ST_RETRY;
-            init_graph(A, S, seq, len, creator0, lane);
+            init_graph<TRACE>(A, S, seq, len, creator0, lane);
             N = len + 2; E = len + 1;
             for (int t = lane; t < len; t += 32) {
-                if (tr_aln) tr_aln[t] = -1;
-                if (tr_node) tr_node[t] = creator0 + t;
+                if constexpr (TRACE) { tr_aln[t] = -1; tr_node[t] = creator0 + t; }
             }
             continue;
         }
@@ -109,9 +109,7 @@ __device__ __forceinline__ int process_group(const KernelArgs &A, int slot, int 
             st[SI_T_DP] += tk0 - tk1;
             st[SI_CELLS] += R.cells; st[SI_INTOPS] += R.intops; st[SI_FULL] += R.full; st[SI_ALN] += 1;
             st[R.bits == 16 ? SI_ALN16 : SI_ALN32] += 1; st[SI_TB] += R.tbbytes;
-            if (A.tr_score) A.tr_score[r] = R.best_score;
-            if (A.tr_bits) A.tr_bits[r] = R.bits;
-            if (A.tr_cells) A.tr_cells[r] = (long long)R.cells;
+            if constexpr (TRACE) { A.tr_score[r] = R.best_score; A.tr_bits[r] = R.bits; A.tr_cells[r] = (long long)R.cells; }
         }
         __syncwarp();
         bool ok;
@@ -146,7 +144,7 @@ __host__ __device__ constexpr int variant_warp_words(int wcap) {
     return (V == 0 ? RING * 3 * wcap + RING * 4 : ring16_warp_words<(V == 0 ? 2 : V)>()) + 32;
 }
 
-template <int V>
+template <int V, bool TRACE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (V == 2 ? MPOA_V2_BLOCKS : V == 4 ? MPOA_V4_BLOCKS : V == 8 ? 3 : 3))
 poa_group_kernel(const __grid_constant__ KernelArgs A) {
     extern __shared__ __align__(16) int smem[];
@@ -177,8 +175,8 @@ poa_group_kernel(const __grid_constant__ KernelArgs A) {
         }
         const long long tg0 = clock64();
         int rc;
-        if constexpr (V == 0) rc = process_group<V>(A, slot, g, ring, ring_info, lane, gst);
-        else rc = process_group<V>(A, slot, g, ring, nullptr, lane, gst);
+        if constexpr (V == 0) rc = process_group<V, TRACE>(A, slot, g, ring, ring_info, lane, gst);
+        else rc = process_group<V, TRACE>(A, slot, g, ring, nullptr, lane, gst);
         if (lane == 0) {
             A.status[g] = rc;
             if (rc != ST_OK) A.cons_len[g] = 0;
@@ -252,14 +250,16 @@ cudaError_t launch_gather(const uint8_t *cons, const int64_t *region_off, const 
 }
 
 template <int V>
-static const void *variant_fn() { return reinterpret_cast<const void *>(&poa_group_kernel<V>); }
+static const void *variant_fn(bool trace) {
+    return trace ? reinterpret_cast<const void *>(&poa_group_kernel<V, true>) : reinterpret_cast<const void *>(&poa_group_kernel<V, false>);
+}
 
-static const void *kernel_of(int variant) {
+static const void *kernel_of(int variant, bool trace) {
     switch (variant) {
-        case 2: return variant_fn<2>();
-        case 4: return variant_fn<4>();
-        case 8: return variant_fn<8>();
-        default: return variant_fn<0>();
+        case 2: return variant_fn<2>(trace);
+        case 4: return variant_fn<4>(trace);
+        case 8: return variant_fn<8>(trace);
+        default: return variant_fn<0>(trace);
     }
 }
 
@@ -279,7 +279,7 @@ size_t poa_smem_bytes(int variant, int wcap, int warps_per_block) {
 
 cudaError_t launch_poa(int variant, const KernelArgs &A, int n_blocks, int warps_per_block, cudaStream_t stream) {
     const size_t smem = poa_smem_bytes(variant, A.wcap, warps_per_block);
-    const void *fn = kernel_of(variant);
+    const void *fn = kernel_of(variant, A.tr_aln != nullptr);   // all five trace arrays are set together
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     void *args[] = {const_cast<KernelArgs *>(&A)};
@@ -289,7 +289,7 @@ cudaError_t launch_poa(int variant, const KernelArgs &A, int n_blocks, int warps
 int poa_max_blocks_per_sm(int variant, int wcap, int warps_per_block) {
     int nb = 0;
     const size_t smem = poa_smem_bytes(variant, wcap, warps_per_block);
-    const void *fn = kernel_of(variant);
+    const void *fn = kernel_of(variant, false);
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, warps_per_block * 32, smem) != cudaSuccess) return 0;
     return nb;

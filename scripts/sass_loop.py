@@ -10,7 +10,7 @@ V = sys.argv[1] if len(sys.argv) > 1 and sys.argv[1].isdigit() else "4"
 verbose = "-v" in sys.argv
 txt = subprocess.run(["cuobjdump", "-sass", "mandalorion_b200/libmandalorion_poa.so"], capture_output=True, text=True).stdout
 funcs = re.split(r"\n\s*Function : ", txt)
-body = next(f for f in funcs if f.startswith("_ZN4mpoa16poa_group_kernelILi%sEEE" % V))
+body = next(f for f in funcs if f.startswith("_ZN4mpoa16poa_group_kernelILi%sELb0EEE" % V))
 ins = []
 for ln in body.splitlines():
     m = re.match(r"\s*/\*([0-9a-f]{4,6})\*/\s+(.*?);", ln)

@@ -34,7 +34,7 @@ for ln in txt.splitlines():
         continue
     m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
     if m:
-        on = ("poa_group_kernelILi%sE" % V) in m.group(1)
+        on = ("poa_group_kernelILi%sELb0E" % V) in m.group(1)
         continue
     if on and re.match(r"\s+/\*[0-9a-f]{4,6}\*/", ln) and cur:
         cnt[phase(*cur)] += 1

@@ -42,6 +42,9 @@ def both(gpu_ctx, groups, params=None):
     got = gpu_ctx.consensus_batch(packed=packed, trace=True)
     assert got["stats"]["n_kernel_launches"] >= 1       # the CUDA kernels ran: nothing else can produce output
     assert_same(got, want, packed)
+    # the production instantiation of the kernel (no trace outputs compiled in) must agree as well
+    plain = gpu_ctx.consensus_batch(packed=packed)
+    assert_same(plain, want, packed, check_trace=False)
     return got, want
 
 
