@@ -497,6 +497,7 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                 p0 = __shfl_sync(FULL, m_p0, l);
                 if (npre == 255) npre = (int)in_off[i + 1] - in0;
                 left = N; right = 0; minb = INT_MAX; maxe = -1;
+#pragma unroll 1
                 for (int k = 0; k < npre; ++k) {
                     const int p = k == 0 ? p0 : (int)in_row[in0 + k];
                     int bs, es, pl, pr;
@@ -541,6 +542,7 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
                 extra += (uint32_t)max(0, npre - 1) * B.width;
 #pragma unroll
                 for (int m = 0; m < WPL; ++m) { M2[m] = NEG2; EA[m] = NEG2; EB[m] = NEG2; }
+#pragma unroll 1
                 for (int k = 0; k < npre; ++k) {
                     const int p = k == 0 ? p0 : (int)in_row[in0 + k];
                     int bs, es;

@@ -120,7 +120,9 @@ __device__ __forceinline__ void remain_pass(const KernelArgs &A, const Slot &S, 
         if (active) {
             const uint32_t o0 = out_off[r], o1 = out_off[r + 1];
             int maxw = -1;
-            for (uint32_t e = o0; e < o1; ++e) {
+#pragma unroll 1
+    #pragma unroll 1
+        for (uint32_t e = o0; e < o1; ++e) {
                 const int t = (int)out_row[e], w = out_w[e];
                 if (w > maxw) { maxw = w; hs = t; }
                 tosink |= (t == N - 1);
@@ -214,6 +216,7 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
                     if (br_[u] == b) { v[u] = r; key[u] = r + (sr_[u] & 15); }
                     else {                    // rare: look for the base among the aligned siblings
                         const int sb = sr_[u], before = sb >> 4, after = sb & 15;
+#pragma unroll 1
                         for (int x = r - before; x <= r + after; ++x)
                             if (x != r && base[x] == b) v[u] = x;
                         if (v[u] < 0) { isnew[u] = 1; sibof[u] = r; key[u] = r + after; }
@@ -242,6 +245,7 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
                 if (isnew[u]) atomicAdd(&cnt[ks], 1);
                 if (sibof[u] >= 0) {
                     const int sb = sib[sibof[u]];
+#pragma unroll 1
                     for (int x = sibof[u] - (sb >> 4); x <= sibof[u] + (sb & 15); ++x) grow[x] = 1;
                 }
             }
@@ -333,6 +337,7 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
                 if (o1[u] > o0[u]) {
                     if (e0[u] == to_old[u]) { out_w[o0[u]] = w0[u] + 1; found = true; }
                     else {
+#pragma unroll 1
                         for (uint32_t e = o0[u] + 1; e < o1[u]; ++e)
                             if ((int)out_row[e] == to_old[u]) { out_w[e] += 1; found = true; break; }
                     }
@@ -424,6 +429,7 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
                     if (sr >= 0) {
                         if (nin_old[u] > 0) n_in_row[io++] = xa[u];
                         if (nin_old[u] > 1) n_in_row[io++] = xb[u];
+#pragma unroll 1
                         for (int e = 2; e < nin_old[u]; ++e) {
                             const int x = (int)in_row[i0[u] + e];
                             n_in_row[io++] = x + cnt[x];
@@ -431,6 +437,7 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
                         if (ai[u] >= 0) n_in_row[io++] = ai[u];
                         if (nout_old[u] > 0) { n_out_row[oo] = ya[u]; n_out_w[oo++] = wa[u]; }
                         if (nout_old[u] > 1) { n_out_row[oo] = yb[u]; n_out_w[oo++] = wb[u]; }
+#pragma unroll 1
                         for (int e = 2; e < nout_old[u]; ++e) {
                             const int y = (int)out_row[o0[u] + e];
                             n_out_row[oo] = y + cnt[y];
@@ -480,7 +487,9 @@ __device__ __forceinline__ int heaviest_bundle(const KernelArgs &A, const Slot &
         int max_id = -1;
         if (r == 0) {
             int path_score = -1, path_max_w = -1;
-            for (uint32_t e = o0; e < o1; ++e) {
+#pragma unroll 1
+    #pragma unroll 1
+        for (uint32_t e = o0; e < o1; ++e) {
                 const int t = (int)out_row[e], w = out_w[e];
                 if (w > path_max_w || (w == path_max_w && score[t] > path_score)) {
                     max_id = t; path_score = score[t]; path_max_w = w;
@@ -488,7 +497,9 @@ __device__ __forceinline__ int heaviest_bundle(const KernelArgs &A, const Slot &
             }
         } else {
             int max_w = INT_MIN;
-            for (uint32_t e = o0; e < o1; ++e) {
+#pragma unroll 1
+    #pragma unroll 1
+        for (uint32_t e = o0; e < o1; ++e) {
                 const int t = (int)out_row[e], w = out_w[e];
                 if (max_w < w) { max_w = w; max_id = t; }
                 else if (max_w == w && score[max_id] <= score[t]) max_id = t;

@@ -74,6 +74,7 @@ __device__ __forceinline__ int hhat_cell(const KernelArgs &A, const Slot &S, con
     const uint32_t *in_off = in_off_p(A, S), *in_row = in_row_p(A, S);
     const int in0 = (int)in_off[i], npre = (int)in_off[i + 1] - in0;
     int mx = NEG, e1 = NEG, e2 = NEG;
+#pragma unroll 1
     for (int kk = 0; kk < npre; ++kk) {
         const int p = (int)in_row[in0 + kk];
         const RowView<T> vp = row_view<T>(A, S, p, lg, qlen);
@@ -95,6 +96,7 @@ __device__ __forceinline__ void f_values(const KernelArgs &A, const Slot &S, con
                                          const uint8_t *__restrict__ q, int qlen, int lg, int lane, int f[4]) {
     const DevParams &P = A.P;
     int f1j = NEG, f2j = NEG, f1m = NEG, f2m = NEG;
+#pragma unroll 1
     for (int k = vi.beg + lane; k <= j - 1; k += 32) {
         const int hk = hhat_cell<T>(A, S, vi, i, k, nbase, q, qlen, lg);
         f1j = max(f1j, hk - P.oe1 - P.e1 * (j - 1 - k));
@@ -201,6 +203,7 @@ __device__ __forceinline__ bool traceback(const KernelArgs &A, const Slot &S, co
         /* The predecessors are probed by one lane each (32 at a time); the FIRST one in edge order
          * that qualifies is taken, exactly like abPOA's loop over pre_id. */
         if (cur_op & OP_M) {
+#pragma unroll 1
             for (int k0 = 0; k0 < npre && !hit; k0 += 32) {
                 const int k = k0 + lane;
                 int p = 0;
@@ -220,6 +223,7 @@ __device__ __forceinline__ bool traceback(const KernelArgs &A, const Slot &S, co
         }
         if (!hit && (cur_op & OP_E)) {
             const int e1ij = rv_get(vi, 1, j), e2ij = rv_get(vi, 2, j);
+#pragma unroll 1
             for (int k0 = 0; k0 < npre && !hit; k0 += 32) {
                 const int k = k0 + lane;
                 int p = 0, nop = 0;
