@@ -375,6 +375,7 @@ __device__ __forceinline__ int dp_align16(const KernelArgs &A, const Slot &S, in
      * of cells 2w and 2w+1 against node base b.  A lane that re-binds copies its words from here. */
     uint32_t *qprof = qprof_p(A, S);
     const int qps = (int)qprof_stride(A.L.qcap);
+#pragma unroll 1
     for (int wd = lane; wd <= (qlen >> 1); wd += 32) {
         const int qa = q[max(2 * wd - 1, 0)], qc = q[min(2 * wd, qlen - 1)];
 #pragma unroll

@@ -186,6 +186,7 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
     const int32_t *qmap = qmap_p(A, S), *creator = creator_p(A, S);
     uint8_t *grow = grow_p(A, S);
 
+#pragma unroll 1
     for (int r = lane; r < N; r += 32) { cnt[r] = 0; addin[r] = -1; addout[r] = -1; grow[r] = 0; }
     __syncwarp();
 
@@ -482,6 +483,7 @@ __device__ __forceinline__ int heaviest_bundle(const KernelArgs &A, const Slot &
     int32_t *score = cnt_p(A, S), *maxout = addin_p(A, S);
     score[N - 1] = 0;
     maxout[N - 1] = -1;
+#pragma unroll 1
     for (int r = N - 2; r >= 0; --r) {
         const uint32_t o0 = out_off[r], o1 = out_off[r + 1];
         int max_id = -1;
@@ -509,6 +511,7 @@ __device__ __forceinline__ int heaviest_bundle(const KernelArgs &A, const Slot &
         maxout[r] = max_id;
     }
     int len = 0, curr = maxout[0];
+#pragma unroll 1
     while (curr != N - 1 && curr >= 0) {
         if (len >= cap) return -1;
         cons[len++] = "ACGTN"[base_p(A, S)[curr]];

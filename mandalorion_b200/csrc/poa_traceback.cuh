@@ -122,6 +122,7 @@ __device__ __forceinline__ bool traceback(const KernelArgs &A, const Slot &S, co
     int32_t *qmap = qmap_p(A, S);
     const int lg = R.lgpn;
     int i = R.best_i, j = R.best_j, cur_op = OP_ALL;
+#pragma unroll 1
     for (int t = j + lane; t < qlen; t += 32) qmap[t] = -1;
     int4 *winfo = reinterpret_cast<int4 *>(scratch);          // [TBW] rowinfo of rows i, i-1, ...
     uint4 *wtb = reinterpret_cast<uint4 *>(scratch) + TBW;    // [TBW] rowtb
@@ -276,6 +277,7 @@ __device__ __forceinline__ bool traceback(const KernelArgs &A, const Slot &S, co
         }
         if (!hit) return false;
     }
+#pragma unroll 1
     for (int t = lane; t < j; t += 32) qmap[t] = -1;
     __syncwarp();
     return true;
