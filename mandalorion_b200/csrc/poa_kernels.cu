@@ -19,7 +19,7 @@
 #define MPOA_V2_BLOCKS 5
 #endif
 #ifndef MPOA_V4_BLOCKS
-#define MPOA_V4_BLOCKS 4
+#define MPOA_V4_BLOCKS 5
 #endif
 
 namespace mpoa {
