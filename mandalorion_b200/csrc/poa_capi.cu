@@ -225,18 +225,31 @@ extern "C" int mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups, const int64_t 
         ctx->err = "bad read_base_off / bases";
         return MPOA_EINVAL;
     }
+    /* the one big copy (the bases, from the caller's buffer) is issued first: the host-side pass over
+     * the offsets below runs while it is in flight */
+    cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;
+    CK(cudaEventRecord(e0, ctx->stream));
+    const size_t nb = (size_t)std::max<int64_t>(n_bases, 16);
+    CK(ctx->b_ascii.ensure(nb)); CK(ctx->b_codes.ensure(nb));
+    uint8_t *d_ascii = (uint8_t *)ctx->b_ascii.p;
+    if (n_bases > 0) CK(cudaMemcpyAsync(d_ascii, bases, n_bases, cudaMemcpyHostToDevice, ctx->stream));
+    auto fail = [&](const char *msg) {      // the caller's buffer must not be read after we return
+        cudaStreamSynchronize(ctx->stream);
+        ctx->err = msg;
+        return (int)MPOA_EINVAL;
+    };
     ctx->h_gro.assign(group_read_off, group_read_off + n_groups + 1);
     ctx->h_rbo.assign(read_base_off, read_base_off + n_reads + 1);
     ctx->ginfo.resize(n_groups);
     for (int64_t g = 0; g < n_groups; ++g) {
         GroupInfo &gi = ctx->ginfo[g];
         const int64_t r0 = ctx->h_gro[g], r1 = ctx->h_gro[g + 1];
-        if (r1 < r0 || r1 > n_reads) { ctx->err = "group_read_off not monotone"; return MPOA_EINVAL; }
+        if (r1 < r0 || r1 > n_reads) return fail("group_read_off not monotone");
         gi.n_reads = (int32_t)(r1 - r0);
         gi.maxlen = 0; gi.minlen = INT_MAX; gi.sumlen = 0;
         for (int64_t r = r0; r < r1; ++r) {
             const int64_t len = ctx->h_rbo[r + 1] - ctx->h_rbo[r];
-            if (len < 0 || len > (1 << 26)) { ctx->err = "bad read length"; return MPOA_EINVAL; }
+            if (len < 0 || len > (1 << 26)) return fail("bad read length");
             gi.maxlen = std::max<int32_t>(gi.maxlen, (int32_t)len);
             gi.minlen = std::min<int32_t>(gi.minlen, (int32_t)len);
             gi.sumlen += len;
@@ -258,21 +271,15 @@ extern "C" int mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups, const int64_t 
     }
     ctx->n_groups = n_groups; ctx->n_reads = n_reads; ctx->n_bases = n_bases;
 
-    cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;
-    CK(cudaEventRecord(e0, ctx->stream));
-    const size_t nb = (size_t)std::max<int64_t>(n_bases, 16);
-    CK(ctx->b_ascii.ensure(nb)); CK(ctx->b_codes.ensure(nb));
     CK(ctx->b_rbo.ensure((n_reads + 1) * sizeof(int64_t))); CK(ctx->b_gro.ensure((n_groups + 1) * sizeof(int64_t)));
     CK(ctx->b_region.ensure((n_groups + 1) * sizeof(int64_t)));
     CK(ctx->b_len.ensure(n_groups * sizeof(int32_t))); CK(ctx->b_status.ensure(n_groups * sizeof(int32_t)));
     CK(ctx->b_queue.ensure(n_groups * sizeof(int32_t)));
-    uint8_t *d_ascii = (uint8_t *)ctx->b_ascii.p;
     ctx->d_codes = (uint8_t *)ctx->b_codes.p;
     ctx->d_rbo = (int64_t *)ctx->b_rbo.p; ctx->d_gro = (int64_t *)ctx->b_gro.p; ctx->d_region_off = (int64_t *)ctx->b_region.p;
     /* the ASCII input is dead once it is encoded: its buffer becomes the consensus regions */
     ctx->d_cons = d_ascii;
     ctx->d_cons_len = (int32_t *)ctx->b_len.p; ctx->d_status = (int32_t *)ctx->b_status.p; ctx->d_queue = (int32_t *)ctx->b_queue.p;
-    if (n_bases > 0) CK(cudaMemcpyAsync(d_ascii, bases, n_bases, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_rbo, ctx->h_rbo.data(), (n_reads + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_gro, ctx->h_gro.data(), (n_groups + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     /* consensus region of a group = the byte range of its reads: a consensus is a path of the
