@@ -28,7 +28,7 @@ namespace mpoa {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NEG = -(1 << 28);      // -inf surrogate in int32 arithmetic
 constexpr int NEG16 = -30000;        // -inf surrogate / floor of the packed int16 path
-constexpr int RING = 8;              // rows kept in the shared-memory ring
+constexpr int RING = 4;              // rows kept in the shared-memory ring of the int32 variant (occupancy: 3*wcap ints per row)
 constexpr int WARPS_PER_BLOCK = 4;
 
 enum GroupStatus : int { ST_OK = 0, ST_EMPTY = 1, ST_RETRY = 2, ST_PENDING = 3, ST_RETRY_WIDE = 4, ST_RETRY_32 = 5 };
