@@ -151,6 +151,7 @@ __device__ __forceinline__ int dp_align32(const KernelArgs &A, const Slot &S, in
                 left = min(N, prev_info.z + 1); right = max(0, prev_info.w + 1);
                 minb = prev_info.x; maxe = prev_info.y;
             } else {
+#pragma unroll 1
                 for (int k = 0; k < npre; ++k) {
                     const int p = k == 0 ? p0 : (int)in_row[in0 + k];
                     const int4 pi = (p == i - 1) ? prev_info : ((i - p < RING) ? ring_info[p & (RING - 1)] : rowinfo_p(A, S)[p]);
@@ -178,6 +179,7 @@ __device__ __forceinline__ int dp_align32(const KernelArgs &A, const Slot &S, in
                 const int j = dp_beg + col;
                 const bool cv = col < width;
                 int mx = NEG, ei1 = NEG, ei2 = NEG;
+#pragma unroll 1
                 for (int k = 0; k < npre; ++k) {
                     const int p = k == 0 ? p0 : (int)in_row[in0 + k];
                     const bool near = i - p < RING;

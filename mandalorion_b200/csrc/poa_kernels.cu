@@ -18,6 +18,9 @@
 #ifndef MPOA_V2_BLOCKS
 #define MPOA_V2_BLOCKS 5
 #endif
+#ifndef MPOA_V0_BLOCKS
+#define MPOA_V0_BLOCKS 3
+#endif
 #ifndef MPOA_V4_BLOCKS
 #define MPOA_V4_BLOCKS 5
 #endif
@@ -145,7 +148,7 @@ __host__ __device__ constexpr int variant_warp_words(int wcap) {
 }
 
 template <int V, bool TRACE>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (V == 2 ? MPOA_V2_BLOCKS : V == 4 ? MPOA_V4_BLOCKS : V == 8 ? 3 : 3))
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (V == 2 ? MPOA_V2_BLOCKS : V == 4 ? MPOA_V4_BLOCKS : V == 8 ? 3 : MPOA_V0_BLOCKS))
 poa_group_kernel(const __grid_constant__ KernelArgs A) {
     extern __shared__ __align__(16) int smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
