@@ -42,6 +42,10 @@ extern "C" {
 #define MPOA_GROUP_EMPTY    1  /* no consensus (abpoa would have printed nothing or died):
                                   caller falls back to the first read, reference
                                   utils/SpliceDefineConsensus.py:924-925 */
+#define MPOA_GROUP_TOO_BIG  2  /* no consensus because the group outgrew every device capacity
+                                  (band wider than 4096 cells, workspace larger than the free
+                                  memory): NOT something abpoa would have done -- the caller
+                                  decides (the Python layer falls back like for EMPTY and warns) */
 
 /* group_flags bits */
 #define MPOA_FLAG_SEED   1u    /* the reference would have passed -S (median read length

@@ -21,9 +21,10 @@
 
 namespace mpoa {
 cudaError_t launch_encode(const uint8_t *ascii, uint8_t *codes, int64_t n, cudaStream_t stream);
-cudaError_t launch_poa(int variant, const KernelArgs &A, int n_blocks, int warps_per_block, cudaStream_t stream);
-int poa_max_blocks_per_sm(int variant, int wcap, int warps_per_block);
-size_t poa_smem_bytes(int variant, int wcap, int warps_per_block);
+cudaError_t launch_poa(int code, const KernelArgs &A, int n_blocks, int warps_per_block, cudaStream_t stream);
+int poa_max_blocks_per_sm(int code, int wcap, int warps_per_block);
+size_t poa_smem_bytes(int code, int wcap, int warps_per_block);
+bool variant_exists(int code);
 cudaError_t launch_int_peak(uint32_t *out, int blocks, int iters, cudaStream_t stream);
 cudaError_t launch_gather(const uint8_t *cons, const int64_t *region_off, const int64_t *out_off, uint8_t *out,
                           int64_t n_groups, cudaStream_t stream);
@@ -36,7 +37,7 @@ struct GroupInfo {
     int64_t sumlen;
     double cost;
     int32_t wneed;     // expected band width in cells
-    int8_t lanes16;    // 1: every alignment is expected to fit abPOA's int16 lanes
+    int8_t lanes16;    // 1: the packed int16x2 kernels may run the group (cleared by ST_RETRY_32: junk reads, exotic parameters)
     int8_t level;      // index into kLevels (kernel variant + band capacity) of the next launch
     int8_t attempt;    // workspace-capacity escalation
 };
@@ -82,8 +83,8 @@ struct mpoa_ctx {
     DevBuf b_ascii, b_codes, b_rbo, b_gro, b_region, b_len, b_status, b_queue, b_out_off, b_out;
     DevBuf b_tr_score, b_tr_bits, b_tr_cells, b_tr_aln, b_tr_node;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaStream_t side[16] = {nullptr};
-    cudaEvent_t fork_ev = nullptr, join_ev[16] = {nullptr};
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     double h2d_ms = 0;
     bool ran = false;
     std::vector<int32_t> h_status;
@@ -163,10 +164,8 @@ extern "C" void mpoa_destroy(mpoa_ctx *ctx) {
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
-    for (int k = 0; k < 16; ++k) {
-        if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
-        if (ctx->join_ev[k]) cudaEventDestroy(ctx->join_ev[k]);
-    }
+    if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     delete ctx;
 }
 
@@ -255,18 +254,15 @@ extern "C" int mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups, const int64_t 
             gi.sumlen += len;
         }
         if (gi.n_reads == 0) gi.minlen = 0;
-        /* expected band: 2w + length spread + SIMD rounding on both sides + slack */
+        /* widest band row seen on calibration sets (oracle, every named config): never more than
+         * 2w+1 + length spread + two SIMD vectors of rounding */
         const int w = ctx->params.wb + (int)(ctx->params.wf * (float)gi.maxlen);
-        /* widest row seen on calibration sets: 2w+1 + length spread + two SIMD vectors of rounding */
-        gi.wneed = 2 * w + 1 + (gi.maxlen - gi.minlen) + 2 * ctx->params.simd_pn_i16 + 4;
+        gi.wneed = 2 * w + 1 + (gi.maxlen - gi.minlen) + 2 * ctx->params.simd_pn_i16;
         gi.wneed = std::min(gi.wneed, gi.maxlen + 1 + 2 * ctx->params.simd_pn_i16);
         gi.cost = (double)gi.sumlen * (double)gi.wneed;
-        /* abPOA's own rule for int16 lanes (scores and gap-extended lengths below 32767 minus slack) */
-        const mpoa_params &pp = ctx->params;
-        const int64_t slack = 32767 - std::abs(pp.mismatch) - pp.gap_open1 - pp.gap_ext1 - pp.gap_open2 - pp.gap_ext2;
-        const int64_t est_nodes = (int64_t)(gi.maxlen * (1.0 + 0.02 * gi.n_reads)) + 16 * gi.n_reads + 64;
-        gi.lanes16 = ((int64_t)gi.maxlen * std::abs(pp.match) <= slack &&
-                      std::max<int64_t>(gi.maxlen, est_nodes) * pp.gap_ext1 + pp.gap_open1 <= slack) ? 1 : 0;
+        /* the packed kernels keep scores relative to the diagonal, so they serve abPOA's int16 AND int32
+         * lane widths; a group leaves them only when the kernel itself asks for it (ST_RETRY_32) */
+        gi.lanes16 = 1;
         gi.level = 0; gi.attempt = 0;
     }
     ctx->n_groups = n_groups; ctx->n_reads = n_reads; ctx->n_bases = n_bases;
@@ -309,7 +305,8 @@ extern "C" int mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups, const int64_t 
 struct Caps {
     uint32_t ncap, ecap, qcap;
     uint64_t tbcap;
-    int wcap, variant;
+    int wcap, T, WPL;     // band capacity in cells, team size, words per lane (0: int32 lanes)
+    int code() const { return variant_code(T, WPL); }
 };
 
 static uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
@@ -337,23 +334,14 @@ static SlotLayout make_layout(const Caps &c) {
     return L;
 }
 
-/* launch levels: kernel variant (0 = int32 lanes, 2/4/8 = packed int16x2 words per lane) and the
- * band capacity in cells.  A group escalates along this list when its band or scores outgrow
- * the level it was scheduled at. */
-struct Level { int variant, wcap; };
-static const Level kLevels[] = {{2, 128}, {4, 256}, {8, 512}, {0, 256}, {0, 512}, {0, 1024}, {0, 2048}, {0, 4096},
-                                {0, 8192}, {0, 16384}};
+/* launch levels: kernel variant (team size T, words per lane WPL of the packed int16x2 DP; WPL 0 =
+ * int32 lanes) and the band capacity in cells.  A group escalates along this list when its band
+ * or its scores outgrow the level it ran at.  The int32 ring (RING x 3 x wcap ints per warp) limits
+ * the widest band to 4096 cells; wider groups are reported as MPOA_GROUP_TOO_BIG. */
+struct Level { int T, WPL, wcap; };
+static const Level kLevels[] = {{32, 2, 128}, {32, 4, 256}, {32, 8, 512},
+                                {32, 0, 256}, {32, 0, 512}, {32, 0, 1024}, {32, 0, 2048}, {32, 0, 4096}};
 static const int kNumLevels = (int)(sizeof(kLevels) / sizeof(kLevels[0]));
-
-static int first_level(bool lanes16, int wneed) {
-    for (int l = 0; l < kNumLevels; ++l)
-        if ((lanes16 || kLevels[l].variant == 0) && kLevels[l].wcap >= wneed) return l;
-    return kNumLevels - 1;
-}
-/* can a group scheduled for level a run in a launch of level b? */
-static bool level_covers(int b, int a, bool lanes16) {
-    return kLevels[b].wcap >= kLevels[a].wcap && (kLevels[b].variant == 0 || lanes16);
-}
 
 /* one kernel launch of a round: the groups of one level with one set of capacities */
 struct Launch {
@@ -363,13 +351,12 @@ struct Launch {
     SlotLayout L;
     int wpb = 4, bps = 0;
     int64_t n_blocks = 0;
-    double cost = 0;
     uint64_t ws_off = 0;
     size_t q_off = 0;
-    bool covers[32] = {false};   // levels whose groups this launch may steal
+    bool small = false;          // too few groups to fill the GPU: runs beside the big launches
 };
 
-static void fill_args(mpoa_ctx *ctx, const Launch &ln, int k, KernelArgs &A) {  // steal queues: see run_round
+static void fill_args(mpoa_ctx *ctx, const Launch &ln, int k, KernelArgs &A) {
     std::memset(&A, 0, sizeof(A));
     A.codes = ctx->d_codes; A.read_off = ctx->d_rbo; A.group_read_off = ctx->d_gro;
     A.queue = ctx->d_queue + ln.q_off; A.n_queue = (int)ln.gs.size(); A.queue_head = ctx->d_queue_head + k;
@@ -378,6 +365,7 @@ static void fill_args(mpoa_ctx *ctx, const Launch &ln, int k, KernelArgs &A) {  
     A.stats = ctx->d_stats;
     A.tr_score = ctx->d_tr_score; A.tr_bits = ctx->d_tr_bits; A.tr_cells = ctx->d_tr_cells;
     A.tr_aln = ctx->d_tr_aln; A.tr_node = ctx->d_tr_node;
+    A.level = ln.lv;
     const mpoa_params &p = ctx->params;
     A.P.match = std::abs(p.match); A.P.mismatch = std::abs(p.mismatch);
     A.P.o1 = p.gap_open1; A.P.e1 = p.gap_ext1; A.P.o2 = p.gap_open2; A.P.e2 = p.gap_ext2;
@@ -390,133 +378,108 @@ static void fill_args(mpoa_ctx *ctx, const Launch &ln, int k, KernelArgs &A) {  
     A.K.noe1 = p2(-A.P.oe1, -A.P.oe1); A.K.noe2 = p2(-A.P.oe2, -A.P.oe2);
     A.K.ne1 = p2(-A.P.e1, -A.P.e1); A.K.ne2 = p2(-A.P.e2, -A.P.e2);
     for (int t = 0; t < 16; ++t) A.K.tdec[t] = p2(-A.P.e1 * t, -A.P.e2 * t);
+    A.K.mhop = p2(-A.P.match * 2 * ln.c.WPL, -A.P.match * 2 * ln.c.WPL);
+    A.K.kc_r = (uint32_t)(2 * ln.c.WPL + ((A.P.match * 2 * ln.c.WPL) << 16));
+    A.K.kc_l = (uint32_t)(-2 * ln.c.WPL + ((A.P.match * 2 * ln.c.WPL) << 16));
 }
 
 /*
- * Runs the launches of one round CONCURRENTLY (one stream each): every level gets a share of
- * the resident warps proportional to its estimated cost, so a level with few groups neither
- * waits for the others nor holds the whole GPU.  Groups that cannot be launched at all get
- * ST_EMPTY in h_status.
+ * Runs the launches of one round.  The BIG launches (enough groups to fill the GPU) run one after
+ * the other on the context's stream, widest level first, each with as many persistent blocks as
+ * the GPU holds: launches of different kernel variants that share the SMs were measured at 1.5x
+ * the time of the same work run back to back (the variants evict each other from the instruction
+ * cache).  SMALL launches (a few stragglers of a wide level, the int32 fall-back) occupy a handful
+ * of SMs for as long as their longest group takes: they run beside the big ones on a second
+ * stream, with their own workspace.  Groups that cannot be launched at all get ST_TOO_BIG.
  */
 static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_launch) {
     std::vector<Launch *> live;
-    double tot_cost = 0;
     for (Launch &ln : launches) {
         ln.wpb = 4;
-        while (ln.wpb > 1 && poa_smem_bytes(ln.c.variant, ln.c.wcap, ln.wpb) > ctx->smem_optin) ln.wpb >>= 1;
-        ln.bps = poa_smem_bytes(ln.c.variant, ln.c.wcap, ln.wpb) > ctx->smem_optin
-                     ? 0 : poa_max_blocks_per_sm(ln.c.variant, ln.c.wcap, ln.wpb);
+        while (ln.wpb > 1 && poa_smem_bytes(ln.c.code(), ln.c.wcap, ln.wpb) > ctx->smem_optin) ln.wpb >>= 1;
+        ln.bps = poa_smem_bytes(ln.c.code(), ln.c.wcap, ln.wpb) > ctx->smem_optin
+                     ? 0 : poa_max_blocks_per_sm(ln.c.code(), ln.c.wcap, ln.wpb);
         if (ln.bps <= 0) {
             ctx->err = "band wider than shared memory allows";
-            for (int32_t g : ln.gs) ctx->h_status[g] = ST_EMPTY;
+            for (int32_t g : ln.gs) ctx->h_status[g] = ST_TOO_BIG;
             continue;
         }
         if (const char *b = getenv("MPOA_BPS")) ln.bps = std::min(ln.bps, std::max(1, atoi(b)));   // tuning aid
         ln.L = make_layout(ln.c);
-        ln.cost = 0;
-        for (int32_t g : ln.gs) ln.cost += ctx->ginfo[g].cost;
-        /* per-row cost grows with the words per lane; wider levels are also over-provisioned on
-         * purpose: they finish first and then steal from the narrower ones */
-        ln.cost *= ln.c.variant == 0 ? 6.0 : (ln.c.variant == 2 ? 1.0 : ln.c.variant == 3 ? 1.6 : ln.c.variant == 4 ? 2.2 : 3.5);
-        tot_cost += ln.cost;
         live.push_back(&ln);
     }
     if (live.empty()) return MPOA_OK;
-    if (live.size() > 16) { ctx->err = "too many launch levels"; return MPOA_EINVAL; }
+    std::sort(live.begin(), live.end(), [](const Launch *a, const Launch *b) { return a->lv > b->lv; });
+    const size_t min_groups = (size_t)ctx->n_sm * 16;
+    size_t n_big = 0;
+    for (Launch *ln : live) { ln->small = ln->gs.size() < min_groups; n_big += ln->small ? 0 : 1; }
+    if (n_big == 0) live[0]->small = false;           // nothing to run beside
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     const uint64_t budget = (uint64_t)(((uint64_t)free_b + ctx->ws_bytes) * 0.85);
-    uint64_t need = 0;
+    /* the big launches share one workspace (they run one after the other), every small one has its own */
+    uint64_t need_big = 0, need_small = 0;
     for (Launch *ln : live) {
-        const double share = live.size() == 1 ? 1.0 : std::max(ln->cost / std::max(tot_cost, 1.0), 0.02);
-        int64_t nb = (int64_t)std::max(1.0, share * ln->bps * ctx->n_sm + 0.5);
-        nb = std::min<int64_t>(nb, ((int64_t)ln->gs.size() + ln->wpb - 1) / ln->wpb);
+        const int tpb = ln->wpb * (32 / ln->c.T);     // teams (= workspace slots) per block
+        int64_t nb = (int64_t)ln->bps * ctx->n_sm;
+        nb = std::min<int64_t>(nb, ((int64_t)ln->gs.size() + tpb - 1) / tpb);
+        nb = std::min<int64_t>(nb, (int64_t)((budget / 2) / ((uint64_t)tpb * ln->L.slot_bytes)));
         ln->n_blocks = nb;
-        need += (uint64_t)nb * ln->wpb * ln->L.slot_bytes;
+        const uint64_t bytes = (uint64_t)nb * tpb * ln->L.slot_bytes;
+        if (ln->small) { ln->ws_off = need_small; need_small += bytes; } else need_big = std::max(need_big, bytes);
     }
-    if (need > budget) {
-        const double f = (double)budget / (double)need;
-        need = 0;
-        for (Launch *ln : live) {
-            ln->n_blocks = (int64_t)(ln->n_blocks * f);
-            if (ln->n_blocks <= 0 && (uint64_t)ln->wpb * ln->L.slot_bytes <= budget / live.size()) ln->n_blocks = 1;
-            need += (uint64_t)ln->n_blocks * ln->wpb * ln->L.slot_bytes;
-        }
+    if (need_small > budget / 2) {                    // too much for side by side: everything back to back
+        for (Launch *ln : live) { if (ln->small) need_big = std::max(need_big, (uint64_t)ln->n_blocks * ln->wpb * (32 / ln->c.T) * ln->L.slot_bytes); ln->small = false; }
+        need_small = 0;
     }
+    const uint64_t need = need_big + need_small;
     if (need > ctx->ws_bytes) {
         cudaFree(ctx->d_ws);
         ctx->d_ws = nullptr; ctx->ws_bytes = 0;
         CK(cudaMalloc(&ctx->d_ws, need));
         ctx->ws_bytes = need;
     }
-    uint64_t ws_off = 0;
     size_t q_off = 0;
     std::vector<int32_t> hq;
+    bool any_small = false;
     for (Launch *ln : live) {
-        ln->ws_off = ws_off; ln->q_off = q_off;
-        ws_off += (uint64_t)ln->n_blocks * ln->wpb * ln->L.slot_bytes;
+        ln->ws_off = ln->small ? need_big + ln->ws_off : 0;
+        ln->q_off = q_off;
         q_off += ln->gs.size();
         hq.insert(hq.end(), ln->gs.begin(), ln->gs.end());
+        any_small = any_small || ln->small;
     }
+    if (live.size() > 16) { ctx->err = "too many launch levels"; return MPOA_EINVAL; }
     CK(cudaMemcpyAsync(ctx->d_queue, hq.data(), hq.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_queue_head, 0, 16 * sizeof(int), ctx->stream));
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> vev;
-    std::vector<int> vidx;
-    const bool fork = live.size() > 1;
-    if (fork) {
+    if (any_small) {
+        if (!ctx->side) CK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
         if (!ctx->fork_ev) CK(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+        if (!ctx->join_ev) CK(cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming));
         CK(cudaEventRecord(ctx->fork_ev, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->side, ctx->fork_ev, 0));
     }
+    const bool verbose = getenv("MPOA_VERBOSE") != nullptr;
     for (size_t k = 0; k < live.size(); ++k) {
         Launch *ln = live[k];
         if (ln->n_blocks <= 0) {
             ctx->err = "not enough device memory for one workspace slot";
-            for (int32_t g : ln->gs) ctx->h_status[g] = ST_EMPTY;
+            for (int32_t g : ln->gs) ctx->h_status[g] = ST_TOO_BIG;
             continue;
-        }
-        cudaStream_t st = ctx->stream;
-        if (fork) {
-            if (!ctx->side[k]) CK(cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking));
-            if (!ctx->join_ev[k]) CK(cudaEventCreateWithFlags(&ctx->join_ev[k], cudaEventDisableTiming));
-            st = ctx->side[k];
-            CK(cudaStreamWaitEvent(st, ctx->fork_ev, 0));
         }
         KernelArgs A;
         fill_args(ctx, *ln, (int)k, A);
-        /* work stealing: once its own queue is empty a level drains the queues of the narrower
-         * levels it covers (widest first); its slot capacities were sized for them (see caller) */
-        A.n_steal = 0;
-        for (int o = (int)live.size() - 1; o >= 0 && A.n_steal < 4; --o) {
-            if (o == (int)k || live[o]->n_blocks <= 0) continue;
-            if (!ln->covers[live[o]->lv]) continue;
-            A.steal_queue[A.n_steal] = ctx->d_queue + live[o]->q_off;
-            A.steal_n[A.n_steal] = (int)live[o]->gs.size();
-            A.steal_head[A.n_steal] = ctx->d_queue_head + o;
-            ++A.n_steal;
-        }
-        cudaEvent_t v0 = nullptr, v1 = nullptr;
-        const bool verbose = getenv("MPOA_VERBOSE") != nullptr;
-        if (verbose) { cudaEventCreate(&v0); cudaEventCreate(&v1); cudaEventRecord(v0, st); }
-        CK(launch_poa(ln->c.variant, A, (int)ln->n_blocks, ln->wpb, st));
-        if (verbose) { cudaEventRecord(v1, st); vev.push_back({v0, v1}); vidx.push_back((int)k); }
+        cudaStream_t st = ln->small ? ctx->side : ctx->stream;
+        CK(launch_poa(ln->c.code(), A, (int)ln->n_blocks, ln->wpb, st));
         ++*n_launch;
-        if (fork) {
-            CK(cudaEventRecord(ctx->join_ev[k], st));
-            CK(cudaStreamWaitEvent(ctx->stream, ctx->join_ev[k], 0));
-        }
+        if (verbose)
+            fprintf(stderr, "[mpoa] level T=%d WPL=%d wcap=%d groups=%zu blocks=%lld x %d warps (bps %d) slot=%.1f MB%s\n",
+                    ln->c.T, ln->c.WPL, ln->c.wcap, ln->gs.size(), (long long)ln->n_blocks, ln->wpb, ln->bps,
+                    ln->L.slot_bytes / 1e6, ln->small ? " (side stream)" : "");
     }
-    if (!vev.empty()) {
-        cudaStreamSynchronize(ctx->stream);
-        for (size_t q = 0; q < vev.size(); ++q) {
-            float ms = 0;
-            cudaEventSynchronize(vev[q].second);
-            cudaEventElapsedTime(&ms, vev[q].first, vev[q].second);
-            const Launch *ln = live[vidx[q]];
-            fprintf(stderr, "[mpoa] level V=%d wcap=%d groups=%zu blocks=%lld x %d warps (bps %d) slot=%.1f MB cost=%.3g: %.1f ms\n",
-                    ln->c.variant, ln->c.wcap, ln->gs.size(), (long long)ln->n_blocks, ln->wpb, ln->bps,
-                    ln->L.slot_bytes / 1e6, ln->cost, ms);
-            cudaEventDestroy(vev[q].first); cudaEventDestroy(vev[q].second);
-        }
+    if (any_small) {
+        CK(cudaEventRecord(ctx->join_ev, ctx->side));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0));
     }
     return MPOA_OK;
 }
@@ -537,51 +500,62 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
 
     std::vector<int32_t> pending(ng);
     std::iota(pending.begin(), pending.end(), 0);
+    /* tuning aid: bit l set = packed level l may be scheduled (default: all) */
+    unsigned level_mask = ~0u;
+    if (const char *ml = getenv("MPOA_LEVELS")) level_mask = (unsigned)strtoul(ml, nullptr, 0) | ~0x7u;
+    auto pick_level = [&](const GroupInfo &gi, int wneed) {
+        for (int l = 0; l < kNumLevels; ++l) {
+            if (!((level_mask >> l) & 1u)) continue;
+            if (kLevels[l].WPL != 0 && !gi.lanes16) continue;
+            /* a lane wider than abPOA's vector length may start up to (2*WPL - pn) cells before the band */
+            const int slack = std::max(0, 2 * kLevels[l].WPL - ctx->params.simd_pn_i32);
+            if (kLevels[l].wcap >= wneed + slack) return l;
+        }
+        return kNumLevels - 1;
+    };
     for (int64_t g = 0; g < ng; ++g) {
         GroupInfo &gi = ctx->ginfo[g];
-        gi.level = (int8_t)first_level(gi.lanes16 != 0, ctx->params.debug_small_caps ? 1 : gi.wneed);
-        if (const char *ml = getenv("MPOA_MIN_LEVEL")) {   // tuning aid: schedule everything at >= this level
-            const int m = atoi(ml);
-            if (gi.lanes16 && gi.level < m && m < 3) gi.level = (int8_t)m;
-        }
+        gi.lanes16 = 1;
+        gi.level = (int8_t)pick_level(gi, ctx->params.debug_small_caps ? 1 : gi.wneed);
         gi.attempt = 0;
     }
     int64_t n_launch = 0;
     std::vector<int32_t> dstat(ng);
     for (int round = 0; round < 12 && !pending.empty(); ++round) {
-        /* one launch per level; a level with too few groups to fill the GPU is folded into a
-         * wider level that covers it (launches of one batch are serialised) */
+        /* one launch per level.  A level with fewer groups than the GPU holds teams is folded into
+         * the next wider level of the same lane family when there is one (every group runs correctly
+         * in any level at least as wide as its own); what stays small runs beside the big launches
+         * (run_round) */
         std::vector<std::vector<int32_t>> bins(kNumLevels);
         for (int32_t g : pending) bins[ctx->ginfo[g].level].push_back(g);
-        /* rows cost almost the same in the 128- and 256-cell variants (fixed per-row work dominates)
-         * while a second concurrent launch splits the SMs and leaves stragglers: the narrow packed
-         * level is always run inside the 256-cell launch when there is one */
-        if (!bins[1].empty() && !bins[0].empty() && !getenv("MPOA_NO_FOLD")) { bins[1].insert(bins[1].end(), bins[0].begin(), bins[0].end()); bins[0].clear(); }
-        const size_t min_groups = (size_t)ctx->n_sm;
+        const size_t min_groups = (size_t)ctx->n_sm * 16;
         for (int a = 0; a < kNumLevels; ++a) {
             if (bins[a].empty() || bins[a].size() >= min_groups) continue;
-            bool all16 = true;
-            for (int32_t g : bins[a]) all16 = all16 && ctx->ginfo[g].lanes16;
-            for (int b = 0; b < kNumLevels; ++b) {
-                if (b == a || bins[b].empty() || !level_covers(b, a, all16)) continue;
-                bins[b].insert(bins[b].end(), bins[a].begin(), bins[a].end());
-                bins[a].clear();
-                break;
-            }
+            for (int o = a + 1; o < kNumLevels; ++o)
+                if (!bins[o].empty() && (kLevels[o].WPL == 0) == (kLevels[a].WPL == 0)) {
+                    bins[o].insert(bins[o].end(), bins[a].begin(), bins[a].end());
+                    bins[a].clear();
+                    break;
+                }
         }
         std::vector<Launch> launches;
         for (int lv = 0; lv < kNumLevels; ++lv) {
             auto &gs = bins[lv];
             if (gs.empty()) continue;
+            /* heaviest first (longest-processing-time order keeps the tail of the launch short); for
+             * two teams per warp: longest reads first, so that the groups the teams of one warp work on
+             * at the same time have about the same number of graph rows */
+            const bool by_len = kLevels[lv].T == 16;
             std::sort(gs.begin(), gs.end(), [&](int32_t a, int32_t b) {
-                const double ca = ctx->ginfo[a].cost, cb = ctx->ginfo[b].cost;
-                return ca != cb ? ca > cb : a < b;
+                const GroupInfo &ga = ctx->ginfo[a], &gb = ctx->ginfo[b];
+                if (by_len && ga.maxlen != gb.maxlen) return ga.maxlen > gb.maxlen;
+                return ga.cost != gb.cost ? ga.cost > gb.cost : a < b;
             });
             Caps c;
-            c.wcap = kLevels[lv].wcap; c.variant = kLevels[lv].variant;
+            c.wcap = kLevels[lv].wcap; c.T = kLevels[lv].T; c.WPL = kLevels[lv].WPL;
             uint64_t ncap = 0, qcap = 0, sum_max = 0, tbmax = 0;
             int att_max = 0;
-            const uint64_t cell_bytes = c.variant == 0 ? 12 : 6;
+            const uint64_t cell_bytes = c.WPL == 0 ? 12 : 6;
             for (int32_t g : gs) {
                 const GroupInfo &gi = ctx->ginfo[g];
                 uint64_t est;
@@ -595,7 +569,7 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
                 sum_max = std::max<uint64_t>(sum_max, gi.sumlen);
                 att_max = std::max<int>(att_max, gi.attempt);
                 const uint64_t wrow = std::min<uint64_t>(std::min<uint64_t>(c.wcap, gi.maxlen + 64),
-                                                         gi.attempt == 0 ? (uint64_t)gi.wneed : (uint64_t)c.wcap) + 16;
+                                                         gi.attempt == 0 ? (uint64_t)gi.wneed : (uint64_t)c.wcap) + 32;
                 tbmax = std::max<uint64_t>(tbmax, est * wrow * cell_bytes);
             }
             c.ncap = (uint32_t)std::min<uint64_t>(ncap + 8, 0x7fffff00u);
@@ -608,17 +582,6 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
             launches.back().gs = gs;
             launches.back().c = c;
         }
-        /* a launch may steal the groups of every narrower level of the same lane family that runs
-         * in this round: give it capacities that cover them */
-        for (Launch &a : launches)
-            for (const Launch &b : launches) {
-                if (&a == &b) continue;
-                const bool fam = (a.c.variant == 0) == (b.c.variant == 0);
-                if (!fam || b.c.wcap >= a.c.wcap) continue;
-                a.covers[b.lv] = true;
-                a.c.ncap = std::max(a.c.ncap, b.c.ncap); a.c.ecap = std::max(a.c.ecap, b.c.ecap);
-                a.c.qcap = std::max(a.c.qcap, b.c.qcap); a.c.tbcap = std::max(a.c.tbcap, b.c.tbcap);
-            }
         {
             const int rc = run_round(ctx, launches, &n_launch);
             if (rc < 0) return rc;
@@ -627,23 +590,22 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
         CK(cudaMemcpy(dstat.data(), ctx->d_status, ng * sizeof(int32_t), cudaMemcpyDeviceToHost));
         std::vector<int32_t> next;
         for (int32_t g : pending) {
-            if (ctx->h_status[g] == ST_EMPTY) continue;  // not launchable
+            if (ctx->h_status[g] == ST_EMPTY || ctx->h_status[g] == ST_TOO_BIG) continue;  // not launchable
             GroupInfo &gi = ctx->ginfo[g];
-            if (dstat[g] == ST_RETRY) {
-                if (gi.attempt >= 3) { ctx->h_status[g] = ST_EMPTY; continue; }
+            const int code = dstat[g] & 0xff;
+            /* escalate from the level the group actually RAN at (it may have been folded into, or
+             * stolen by, a wider launch than the one it was scheduled for) */
+            const int ran = std::min(kNumLevels - 1, std::max((int)gi.level, (dstat[g] >> 8) & 0xff));
+            if (code == ST_RETRY) {
+                if (gi.attempt >= 3) { ctx->h_status[g] = ST_TOO_BIG; continue; }
                 gi.attempt++;
+                gi.level = (int8_t)ran;
                 next.push_back(g);
-            } else if (dstat[g] == ST_RETRY_WIDE || dstat[g] == ST_RETRY_32) {
-                int lv = gi.level, nl = -1;
-                if (dstat[g] == ST_RETRY_32) {
-                    gi.lanes16 = 0;
-                    for (int b = 0; b < kNumLevels; ++b)
-                        if (kLevels[b].variant == 0 && kLevels[b].wcap >= kLevels[lv].wcap) { nl = b; break; }
-                } else {
-                    for (int b = 0; b < kNumLevels; ++b)
-                        if (kLevels[b].wcap > kLevels[lv].wcap && (kLevels[b].variant == 0 || gi.lanes16)) { nl = b; break; }
-                }
-                if (nl < 0) { ctx->h_status[g] = ST_EMPTY; continue; }
+            } else if (code == ST_RETRY_WIDE || code == ST_RETRY_32) {
+                if (code == ST_RETRY_32) gi.lanes16 = 0;                       // junk reads / exotic parameters: int32 lanes
+                else gi.wneed = std::max(gi.wneed, kLevels[ran].wcap + 1);     // the band outgrew the level it ran at
+                const int nl = pick_level(gi, gi.wneed);
+                if (kLevels[nl].wcap < gi.wneed) { ctx->h_status[g] = ST_TOO_BIG; continue; }
                 gi.level = (int8_t)nl;
                 next.push_back(g);
             } else ctx->h_status[g] = dstat[g];
@@ -651,7 +613,7 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
         if (round == 0) st.n_retry_groups = (int64_t)next.size();
         pending.swap(next);
     }
-    for (int32_t g : pending) ctx->h_status[g] = ST_EMPTY;  // still too big after the last attempt
+    for (int32_t g : pending) ctx->h_status[g] = ST_TOO_BIG;  // still too big after the last attempt
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
@@ -685,7 +647,7 @@ extern "C" int mpoa_batch_fetch(mpoa_ctx *ctx, int64_t *cons_off, uint8_t *cons_
     for (int64_t g = 0; g < ng; ++g) {
         const bool ok = ctx->h_status[g] == ST_OK;
         cons_off[g + 1] = cons_off[g] + (ok ? len[g] : 0);
-        if (group_status) group_status[g] = ok ? MPOA_GROUP_OK : MPOA_GROUP_EMPTY;
+        if (group_status) group_status[g] = ok ? MPOA_GROUP_OK : ctx->h_status[g] == ST_TOO_BIG ? MPOA_GROUP_TOO_BIG : MPOA_GROUP_EMPTY;
     }
     const int64_t total = cons_off[ng];
     int rc = MPOA_OK;

@@ -22,16 +22,18 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <climits>
 
 namespace mpoa {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NEG = -(1 << 28);      // -inf surrogate in int32 arithmetic
-constexpr int NEG16 = -30000;        // -inf surrogate / floor of the packed int16 path
+constexpr int NEG16 = -28000;        // -inf surrogate / floor of the packed int16 path (per-lane rebased scores, see poa_dp.cuh)
+constexpr int LOW16 = -20000;        // a row whose best rebased score falls below this leaves the packed path (ST_RETRY_32)
 constexpr int RING = 4;              // rows kept in the shared-memory ring of the int32 variant (occupancy: 3*wcap ints per row)
 constexpr int WARPS_PER_BLOCK = 4;
 
-enum GroupStatus : int { ST_OK = 0, ST_EMPTY = 1, ST_RETRY = 2, ST_PENDING = 3, ST_RETRY_WIDE = 4, ST_RETRY_32 = 5 };
+enum GroupStatus : int { ST_OK = 0, ST_EMPTY = 1, ST_RETRY = 2, ST_PENDING = 3, ST_RETRY_WIDE = 4, ST_RETRY_32 = 5, ST_TOO_BIG = 6 };
 
 struct DevParams {
     int match, mismatch, o1, e1, o2, e2, oe1, oe2, wb;
@@ -47,6 +49,8 @@ struct Packed16 {
     uint32_t noe1, noe2;       // (-oe1,-oe1), (-oe2,-oe2): per-word of two cells
     uint32_t ne1, ne2;         // (-e1,-e1), (-e2,-e2)
     uint32_t tdec[16];         // t * (-e1,-e2): decay inside a lane at cell t
+    uint32_t mhop;             // (-match*CPL, -match*CPL): change of score frame between neighbouring lanes
+    uint32_t kc_r, kc_l;       // per lane position: CPL cells and match*CPL of score frame in a row-maximum key (right / left)
 };
 
 /* byte offsets of the arrays inside one warp's HBM workspace ("slot") */
@@ -69,11 +73,6 @@ struct KernelArgs {
     const int32_t *queue;            // group indices to process, heaviest first
     int n_queue;
     int *queue_head;
-    /* queues of NARROWER levels running concurrently: drained once the own queue is empty */
-    int n_steal;
-    const int32_t *steal_queue[4];
-    int steal_n[4];
-    int *steal_head[4];
     uint8_t *ws;                     // n_slots * L.slot_bytes
     SlotLayout L;
     uint8_t *cons;                   // consensus bytes, region of group g at cons_off[g]
@@ -87,6 +86,7 @@ struct KernelArgs {
     DevParams P;
     Packed16 K;
     int wcap;                        // cells per ring row
+    int level;                       // host launch level, reported back with the retry codes
 };
 
 /* words between the base rows of the query profile (one word = the scores of two cells) */
@@ -95,8 +95,72 @@ __host__ __device__ inline uint32_t qprof_stride(uint32_t qcap) { return ((qcap 
 enum StatIdx { SI_CELLS = 0, SI_INTOPS, SI_FULL, SI_ALN, SI_ALN16, SI_ALN32, SI_TB,
                SI_T_PREP, SI_T_DP, SI_T_TB, SI_T_MERGE, SI_T_CONS, SI_T_BUSY, SI_COUNT };
 
-/* kernel variants: 0 = int32 lanes, any band width (chunks of 32 cells);
- * 2/4/8 = packed int16x2, that many 32-bit words (pairs of cells) per lane: band <= 128/256/512 */
-constexpr int kVariants[] = {0, 2, 4, 8};
+/*
+ * A TEAM of T lanes (T = 16: two teams per warp, T = 32: the whole warp) owns one read group.
+ * The two teams of a warp run in LOCKSTEP: every loop that contains a cross-lane operation runs
+ * for the larger of the two teams' trip counts (wmax) and every branch around one is taken by
+ * both or by neither (wany / wall); a team that has nothing to do in an iteration is switched off
+ * by a predicate, never by control flow.  So the whole warp is converged at every shuffle, the
+ * shuffles carry the constant full mask (a run-time member mask costs a MATCH/REDUX/VOTE check per
+ * shuffle) and one instruction stream serves two groups.  Branches and loops WITHOUT cross-lane
+ * operations (per-lane edge lists, re-binding a lane, rare fix-ups) may differ between the teams.
+ */
+template <int T>
+struct Team {
+    static_assert(T == 16 || T == 32, "team size");
+    static constexpr int SIZE = T;
+    int tl;           // lane inside the team
+    int base;         // warp lane of team lane 0
+    __device__ __forceinline__ explicit Team(int warp_lane) {
+        /* warp_lane (0..31) comes through shared memory (poa_group_kernel), so that it stays in a register */
+        tl = T == 32 ? warp_lane : (warp_lane & (T - 1));
+        base = T == 32 ? 0 : (warp_lane & ~(T - 1));
+    }
+    template <typename V> __device__ __forceinline__ V shfl(V v, int src) const { return __shfl_sync(FULL, v, src, T); }
+    template <typename V> __device__ __forceinline__ V shfl_up(V v, int d) const { return __shfl_up_sync(FULL, v, d, T); }
+    template <typename V> __device__ __forceinline__ V shfl_down(V v, int d) const { return __shfl_down_sync(FULL, v, d, T); }
+    template <typename V> __device__ __forceinline__ V shfl_xor(V v, int d) const { return __shfl_xor_sync(FULL, v, d, T); }
+    /* bit l = predicate of team lane l */
+    __device__ __forceinline__ unsigned ballot(bool p) const {
+        if constexpr (T == 32) return __ballot_sync(FULL, p);
+        else return (__ballot_sync(FULL, p) >> base) & 0xffffu;
+    }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    /* maximum over the team */
+    __device__ __forceinline__ int rmax(int v) const {
+        if constexpr (T == 32) return __reduce_max_sync(FULL, v);
+        else {
+            const int a = __reduce_max_sync(FULL, base ? INT_MIN : v), b = __reduce_max_sync(FULL, base ? v : INT_MIN);
+            return base ? b : a;
+        }
+    }
+    /* value of team lane `src`; for a whole warp the REDUX form tells the compiler it is uniform */
+    __device__ __forceinline__ uint32_t pick(uint32_t v, int src) const {
+        if constexpr (T == 32) return __reduce_or_sync(FULL, tl == src ? v : 0u);
+        else return __shfl_sync(FULL, v, src, T);
+    }
+    __device__ __forceinline__ int uniform(int v) const {
+        if constexpr (T == 32) return __reduce_max_sync(FULL, v);
+        else return v;
+    }
+    /* warp-wide agreement between the teams (for T = 32 the argument already is warp-uniform) */
+    __device__ __forceinline__ int wmax(int v) const {
+        if constexpr (T == 32) return v;
+        else return __reduce_max_sync(FULL, v);
+    }
+    __device__ __forceinline__ bool wany(bool p) const {
+        if constexpr (T == 32) return p;
+        else return __any_sync(FULL, p);
+    }
+    __device__ __forceinline__ bool wall(bool p) const {
+        if constexpr (T == 32) return p;
+        else return __all_sync(FULL, p);
+    }
+};
+
+/* kernel variants: team size T and words per lane WPL of the packed int16x2 DP (band <= T*2*WPL
+ * cells); WPL = 0: int32 lanes, one cell per lane, any band width in chunks of 32 (whole warp) */
+struct Variant { int T, WPL; };
+__host__ __device__ constexpr int variant_code(int T, int WPL) { return WPL == 0 ? 0 : T * 100 + WPL; }
 
 }  // namespace mpoa

@@ -43,24 +43,28 @@ MPOA_ACC(uint8_t, grow) MPOA_ACC(uint8_t, tb)
 __device__ __forceinline__ Slot make_slot(const KernelArgs &A, int slot, int par) {
     Slot S;
     S.b = A.ws + (uint64_t)slot * A.L.slot_bytes;
+    asm volatile("" : "+l"(S.b));   // keep the pointer in registers (it is otherwise re-derived at every access)
+    __builtin_assume(__isGlobal(S.b));
     S.par = par;
     return S;
 }
 
-__device__ __forceinline__ int warp_incl_sum(int v, int lane) {
+template <int T>
+__device__ __forceinline__ int team_incl_sum(const Team<T> &tm, int v) {
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(FULL, v, d);
-        if (lane >= d) v += t;
+    for (int d = 1; d < T; d <<= 1) {
+        int t = tm.shfl_up(v, d);
+        if (tm.tl >= d) v += t;
     }
     return v;
 }
 
-__device__ __forceinline__ int warp_incl_max(int v, int lane) {
+template <int T>
+__device__ __forceinline__ int team_incl_max(const Team<T> &tm, int v) {
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(FULL, v, d);
-        if (lane >= d) v = max(v, t);
+    for (int d = 1; d < T; d <<= 1) {
+        int t = tm.shfl_up(v, d);
+        if (tm.tl >= d) v = max(v, t);
     }
     return v;
 }
@@ -82,10 +86,10 @@ enum MetaBits { META_BASE = 7, META_TOSINK = 16 };
 /* ------------------------------------------------------------------------------------------ */
 
 /* first read = linear chain src -> b0 -> ... -> sink, every edge weight 1 */
-template <bool TRACE>
-__device__ __forceinline__ void init_graph(const KernelArgs &A, const Slot &S, const uint8_t *seq, int len, int creator0, int lane) {
+template <int T, bool TRACE>
+__device__ __forceinline__ void init_graph(const KernelArgs &A, const Slot &S, const Team<T> &tm, const uint8_t *seq, int len, int creator0) {
     const int N = len + 2;
-    for (int r = lane; r <= N; r += 32) {
+    for (int r = tm.tl; r <= N; r += T) {
         if (r < N) {
             const bool real = r >= 1 && r <= len;
             base_p(A, S)[r] = real ? seq[r - 1] : 0;
@@ -97,7 +101,7 @@ __device__ __forceinline__ void init_graph(const KernelArgs &A, const Slot &S, c
         in_off_p(A, S)[r] = r == 0 ? 0 : r - 1;
         out_off_p(A, S)[r] = r < N - 1 ? r : N - 1;
     }
-    __syncwarp();
+    /* no cross-lane operation in here: the caller synchronises (the teams of a warp may not both call this) */
 }
 
 /*
@@ -105,42 +109,47 @@ __device__ __forceinline__ void init_graph(const KernelArgs &A, const Slot &S, c
  * reverse BFS computes.  Rows are handled 32 at a time from the sink side; in-window chains are
  * resolved by pointer jumping.  Also emits the per-row meta word used by the DP.
  */
-__device__ __forceinline__ void remain_pass(const KernelArgs &A, const Slot &S, int N, int lane) {
+template <int T>
+__device__ __forceinline__ void remain_pass(const KernelArgs &A, const Slot &S, const Team<T> &tm, int N, bool on) {
+    const int lane = tm.tl;
+    constexpr int LOGT = T == 32 ? 5 : 4;
     const uint32_t *out_off = out_off_p(A, S), *out_row = out_row_p(A, S);
     const int32_t *out_w = out_w_p(A, S);
-    if (lane == 0) {
+    if (on && lane == 0) {
         remain_p(A, S)[N - 1] = -1;
         meta_p(A, S)[N - 1] = 0;
     }
-    int prev_vals = 0;  // remain of rows [w0+32, w0+64)
-    for (int w0 = ((N - 2) / 32) * 32; w0 >= 0; w0 -= 32) {
+    const int nwin = on ? (N - 2) / T + 1 : 0;
+    const int wn = tm.wmax(nwin);
+    int prev_vals = 0;  // remain of rows [w0+T, w0+2T)
+    for (int it = 0; it < wn; ++it) {
+        const int w0 = ((N - 2) / T - it) * T;
         const int r = w0 + lane;
-        const bool active = r <= N - 2;
+        const bool active = it < nwin && r <= N - 2;
         int hs = N - 1, tosink = 0;
         if (active) {
             const uint32_t o0 = out_off[r], o1 = out_off[r + 1];
             int maxw = -1;
 #pragma unroll 1
-    #pragma unroll 1
-        for (uint32_t e = o0; e < o1; ++e) {
+            for (uint32_t e = o0; e < o1; ++e) {
                 const int t = (int)out_row[e], w = out_w[e];
                 if (w > maxw) { maxw = w; hs = t; }
                 tosink |= (t == N - 1);
             }
         }
         int acc, nxt = -1;
-        const int src_prev = min(31, max(0, hs - (w0 + 32)));
-        const int from_prev = __shfl_sync(FULL, prev_vals, src_prev);
+        const int src_prev = min(T - 1, max(0, hs - (w0 + T)));
+        const int from_prev = tm.shfl(prev_vals, src_prev);
         if (!active) acc = 0;
         else if (hs == N - 1) acc = 0;
-        else if (hs >= w0 + 64) acc = remain_p(A, S)[hs] + 1;
-        else if (hs >= w0 + 32) acc = from_prev + 1;
+        else if (hs >= w0 + 2 * T) acc = remain_p(A, S)[hs] + 1;
+        else if (hs >= w0 + T) acc = from_prev + 1;
         else { acc = 1; nxt = hs - w0; }
 #pragma unroll
-        for (int it = 0; it < 5; ++it) {
+        for (int k = 0; k < LOGT; ++k) {
             const int sl = max(nxt, 0);
-            const int a = __shfl_sync(FULL, acc, sl);
-            const int n = __shfl_sync(FULL, nxt, sl);
+            const int a = tm.shfl(acc, sl);
+            const int n = tm.shfl(nxt, sl);
             if (nxt >= 0) { acc += a; nxt = n; }
         }
         if (active) {
@@ -148,7 +157,7 @@ __device__ __forceinline__ void remain_pass(const KernelArgs &A, const Slot &S, 
             meta_p(A, S)[r] = (uint32_t)base_p(A, S)[r] | (tosink ? META_TOSINK : 0);
         }
         prev_vals = acc;
-        __syncwarp();
+        tm.sync();
     }
 }
 
@@ -167,19 +176,27 @@ __device__ __forceinline__ void remain_pass(const KernelArgs &A, const Slot &S, 
  *     of their endpoints (edge order = first-creation order).
  * Returns ST_OK or ST_RETRY (capacity).
  */
-__device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, int &par, int &N, int &E, const uint8_t *__restrict__ q,
-                          int qlen, int creator0, int32_t *tr_aln, int32_t *tr_node, int lane) {
+template <int T>
+__device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, const Team<T> &tm, int &par, int &N_io, int &E_io,
+                                          const uint8_t *__restrict__ q, int qlen_in, int creator0, int32_t *tr_aln, int32_t *tr_node, bool on) {
+    const int lane = tm.tl;
+    /* a team that is switched off walks through the passes with empty ranges */
+    int qlen = on ? qlen_in : 0, N = on ? N_io : 0;
+    int err = ST_OK;
     const uint8_t *__restrict__ base = base_p(A, S), *__restrict__ sib = sib_p(A, S);
     const uint32_t *__restrict__ out_off = out_off_p(A, S), *__restrict__ out_row = out_row_p(A, S);
     const uint32_t *__restrict__ in_off = in_off_p(A, S), *__restrict__ in_row = in_row_p(A, S);
     int32_t *out_w = out_w_p(A, S);
 
-    /* The passes are bound by memory latency, so every pass handles MK*32 elements per iteration and
+    /* The passes are bound by memory latency, so every pass handles MK*T elements per iteration and
      * is written LEVEL BY LEVEL: all loads of one dependency level (for all MK sub-chunks) are issued
      * before anything that depends on them, and no store sits between the levels.  The common case
      * (at most two in- and out-edges per row, a base that matches its aligned node) is covered by the
      * batched levels; the rest falls into short serial loops. */
-    constexpr int MK = 2;
+#ifndef MPOA_MERGE_MK16
+#define MPOA_MERGE_MK16 2
+#endif
+    constexpr int MK = T == 16 ? MPOA_MERGE_MK16 : 2;
     int32_t *cnt = cnt_p(A, S), *addin = addin_p(A, S), *addout = addout_p(A, S), *srcof = srcof_p(A, S);
     int32_t *pv = pv_p(A, S), *pkey = pkey_p(A, S), *pnew = pnew_p(A, S), *psib = psib_p(A, S);
     int32_t *nin = nin_p(A, S), *nout = nout_p(A, S);
@@ -187,17 +204,18 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
     uint8_t *grow = grow_p(A, S);
 
 #pragma unroll 1
-    for (int r = lane; r < N; r += 32) { cnt[r] = 0; addin[r] = -1; addout[r] = -1; grow[r] = 0; }
-    __syncwarp();
+    for (int r = lane; r < N; r += T) { cnt[r] = 0; addin[r] = -1; addout[r] = -1; grow[r] = 0; }
+    tm.sync();
+    const int wq = tm.wmax(qlen);
 
     /* U1: resolve every query base to an existing row or a new node; order keys */
     int carry_key = 0, carry_new = 0;
-    for (int t0 = 0; t0 < qlen; t0 += 32 * MK) {
+    for (int t0 = 0; t0 < wq; t0 += T * MK) {
         int isnew[MK], v[MK], key[MK], sibof[MK];
         int r_[MK], b_[MK], br_[MK], sr_[MK];
 #pragma unroll
         for (int u = 0; u < MK; ++u) {        // level 1: the aligned row and the query base
-            const int t = t0 + u * 32 + lane;
+            const int t = t0 + u * T + lane;
             r_[u] = -1; b_[u] = 0;
             if (t < qlen) { r_[u] = qmap[t]; b_[u] = q[t]; }
         }
@@ -208,7 +226,7 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
         }
 #pragma unroll
         for (int u = 0; u < MK; ++u) {
-            const int t = t0 + u * 32 + lane;
+            const int t = t0 + u * T + lane;
             isnew[u] = 0; v[u] = -1; key[u] = -1; sibof[u] = -1;
             if (t < qlen) {
                 const int r = r_[u];
@@ -233,10 +251,10 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
         }
 #pragma unroll
         for (int u = 0; u < MK; ++u) {
-            const int t = t0 + u * 32 + lane;
-            int ks = warp_incl_max(key[u], lane);
+            const int t = t0 + u * T + lane;
+            int ks = team_incl_max(tm, key[u]);
             ks = max(ks, carry_key);
-            const int incl = warp_incl_sum(isnew[u], lane);
+            const int incl = team_incl_sum(tm, isnew[u]);
             const int nidx = carry_new + incl - isnew[u];
             if (t < qlen) {
                 pv[t] = isnew[u] ? -1 : v[u];
@@ -250,60 +268,61 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
                     for (int x = sibof[u] - (sb >> 4); x <= sibof[u] + (sb & 15); ++x) grow[x] = 1;
                 }
             }
-            carry_key = __shfl_sync(FULL, ks, 31);
-            carry_new += __shfl_sync(FULL, incl, 31);
+            carry_key = tm.shfl(ks, T - 1);
+            carry_new += tm.shfl(incl, T - 1);
         }
     }
     const int n_new = carry_new;
-    const int N2 = N + n_new;
-    if ((uint32_t)N2 > A.L.ncap) return ST_RETRY;
-    __syncwarp();
+    int N2 = N + n_new;
+    if ((uint32_t)N2 > A.L.ncap) { err = ST_RETRY; qlen = 0; N = 0; N2 = 0; }
+    tm.sync();
 
     /* U2: shift[r] = number of new nodes placed before old row r (exclusive scan of cnt) */
     {
         int carry = 0;
-        for (int r0 = 0; r0 < N; r0 += 32 * MK) {
+        const int wn = tm.wmax(N);
+        for (int r0 = 0; r0 < wn; r0 += T * MK) {
             int c[MK];
 #pragma unroll
-            for (int u = 0; u < MK; ++u) { const int r = r0 + u * 32 + lane; c[u] = r < N ? cnt[r] : 0; }
+            for (int u = 0; u < MK; ++u) { const int r = r0 + u * T + lane; c[u] = r < N ? cnt[r] : 0; }
 #pragma unroll
             for (int u = 0; u < MK; ++u) {
-                const int r = r0 + u * 32 + lane;
-                const int incl = warp_incl_sum(c[u], lane);
+                const int r = r0 + u * T + lane;
+                const int incl = team_incl_sum(tm, c[u]);
                 if (r < N) {
                     const int sh = carry + incl - c[u];
                     cnt[r] = sh;
                     srcof[r + sh] = r;
                 }
-                carry += __shfl_sync(FULL, incl, 31);
+                carry += tm.shfl(incl, T - 1);
             }
         }
-        for (int t0 = 0; t0 < qlen; t0 += 32 * MK) {
+        for (int t0 = 0; t0 < qlen; t0 += T * MK) {   // no cross-lane operation in this loop
             int pvv[MK], pk[MK], pn[MK];
 #pragma unroll
             for (int u = 0; u < MK; ++u) {
-                const int t = t0 + u * 32 + lane;
+                const int t = t0 + u * T + lane;
                 pvv[u] = 0; pk[u] = 0; pn[u] = 0;
                 if (t < qlen) { pvv[u] = pv[t]; pk[u] = pkey[t]; pn[u] = pnew[t]; }
             }
 #pragma unroll
             for (int u = 0; u < MK; ++u) {
-                const int t = t0 + u * 32 + lane;
+                const int t = t0 + u * T + lane;
                 if (t < qlen && pvv[u] < 0) srcof[pk[u] + 1 + pn[u]] = -(t + 1);
             }
         }
     }
-    __syncwarp();
+    tm.sync();
 
     /* U3: the path edges u[t-1] -> u[t], t = 0..qlen (u[-1] = source, u[qlen] = sink) */
     int n_new_edges = 0;
-    for (int t0 = 0; t0 <= qlen; t0 += 32 * MK) {
+    for (int t0 = 0; t0 <= qlen && N > 0; t0 += T * MK) {   // no cross-lane operation in this loop
         int from_old[MK], to_old[MK], km[MK], nm[MK], kt[MK], nt[MK];
         int cf[MK], ct[MK], e0[MK], w0[MK];
         uint32_t o0[MK], o1[MK];
 #pragma unroll
         for (int u = 0; u < MK; ++u) {        // level 1: the two path nodes of the edge
-            const int t = t0 + u * 32 + lane;
+            const int t = t0 + u * T + lane;
             from_old[u] = to_old[u] = -2; km[u] = nm[u] = kt[u] = nt[u] = 0;
             if (t <= qlen) {
                 from_old[u] = 0; to_old[u] = N - 1;
@@ -330,7 +349,7 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
         }
 #pragma unroll
         for (int u = 0; u < MK; ++u) {
-            const int t = t0 + u * 32 + lane;
+            const int t = t0 + u * T + lane;
             if (t <= qlen) {
                 const int from_new = from_old[u] >= 0 ? from_old[u] + cf[u] : km[u] + 1 + nm[u];
                 const int to_new = to_old[u] >= 0 ? to_old[u] + ct[u] : kt[u] + 1 + nt[u];
@@ -352,10 +371,10 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
         }
     }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) n_new_edges += __shfl_xor_sync(FULL, n_new_edges, d);
-    const int E2 = E + n_new_edges;
-    if ((uint32_t)E2 > A.L.ecap) return ST_RETRY;
-    __syncwarp();
+    for (int d = T / 2; d > 0; d >>= 1) n_new_edges += tm.shfl_xor(n_new_edges, d);
+    const int E2 = E_io + n_new_edges;
+    if (N > 0 && (uint32_t)E2 > A.L.ecap) { err = ST_RETRY; qlen = 0; N = 0; N2 = 0; }
+    tm.sync();
 
     /* U4: emit the merged graph */
     {
@@ -364,7 +383,8 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
                  *n_out_row = n_out_row_p(A, S);
         int32_t *n_out_w = n_out_w_p(A, S), *n_creator = n_creator_p(A, S);
         uint8_t *n_base = n_base_p(A, S), *n_sib = n_sib_p(A, S);
-        for (int r0 = 0; r0 < N2; r0 += 32 * MK) {
+        const int wn2 = tm.wmax(N2);
+        for (int r0 = 0; r0 < wn2; r0 += T * MK) {
             int din[MK], dout[MK], src[MK], ai[MK], ao[MK], nin_old[MK], nout_old[MK];
             uint32_t i0[MK], o0[MK];
             int xa[MK], xb[MK], ya[MK], yb[MK], wa[MK], wb[MK];      // first two in- / out-edges (+ weights)
@@ -372,13 +392,13 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
             int so[MK];
 #pragma unroll
             for (int u = 0; u < MK; ++u) {    // level 1: which old row (or which new node) lands here
-                const int nr = r0 + u * 32 + lane;
+                const int nr = r0 + u * T + lane;
                 src[u] = 0;
                 if (nr < N2) src[u] = srcof[nr];
             }
 #pragma unroll
             for (int u = 0; u < MK; ++u) {    // level 2: its edge lists, added edges, node bytes
-                const int nr = r0 + u * 32 + lane;
+                const int nr = r0 + u * T + lane;
                 din[u] = dout[u] = 0; ai[u] = ao[u] = -1; i0[u] = o0[u] = 0; nin_old[u] = nout_old[u] = 0;
                 nb[u] = sbv[u] = gr[u] = 0; cre[u] = 0; so[u] = -1;
                 xa[u] = xb[u] = ya[u] = yb[u] = 0; wa[u] = wb[u] = 0;
@@ -416,12 +436,12 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
             }
 #pragma unroll
             for (int u = 0; u < MK; ++u) {
-                const int nr = r0 + u * 32 + lane;
+                const int nr = r0 + u * T + lane;
                 if (nr < N2) {
                     if (src[u] >= 0) { din[u] = nin_old[u] + (ai[u] >= 0); dout[u] = nout_old[u] + (ao[u] >= 0); }
                     else din[u] = dout[u] = 1;
                 }
-                const int iin = warp_incl_sum(din[u], lane), iout = warp_incl_sum(dout[u], lane);
+                const int iin = team_incl_sum(tm, din[u]), iout = team_incl_sum(tm, dout[u]);
                 if (nr < N2) {
                     uint32_t io = carry_in + iin - din[u], oo = carry_out + iout - dout[u];
                     n_in_off[nr] = io;
@@ -460,15 +480,15 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, in
                         if (tr_node) n_creator[nr] = creator0 + t;
                     }
                 }
-                carry_in += __shfl_sync(FULL, iin, 31);
-                carry_out += __shfl_sync(FULL, iout, 31);
+                carry_in += tm.shfl(iin, T - 1);
+                carry_out += tm.shfl(iout, T - 1);
             }
         }
-        if (lane == 0) { n_in_off[N2] = carry_in; n_out_off[N2] = carry_out; }
+        if (lane == 0 && N2 > 0) { n_in_off[N2] = carry_in; n_out_off[N2] = carry_out; }
     }
-    __syncwarp();
-    par ^= 1; N = N2; E = E2;
-    return ST_OK;
+    tm.sync();
+    if (on && err == ST_OK) { par ^= 1; N_io = N2; E_io = E2; }
+    return err;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -490,8 +510,7 @@ __device__ __forceinline__ int heaviest_bundle(const KernelArgs &A, const Slot &
         if (r == 0) {
             int path_score = -1, path_max_w = -1;
 #pragma unroll 1
-    #pragma unroll 1
-        for (uint32_t e = o0; e < o1; ++e) {
+            for (uint32_t e = o0; e < o1; ++e) {
                 const int t = (int)out_row[e], w = out_w[e];
                 if (w > path_max_w || (w == path_max_w && score[t] > path_score)) {
                     max_id = t; path_score = score[t]; path_max_w = w;
@@ -500,8 +519,7 @@ __device__ __forceinline__ int heaviest_bundle(const KernelArgs &A, const Slot &
         } else {
             int max_w = INT_MIN;
 #pragma unroll 1
-    #pragma unroll 1
-        for (uint32_t e = o0; e < o1; ++e) {
+            for (uint32_t e = o0; e < o1; ++e) {
                 const int t = (int)out_row[e], w = out_w[e];
                 if (max_w < w) { max_w = w; max_id = t; }
                 else if (max_w == w && score[max_id] <= score[t]) max_id = t;

@@ -8,22 +8,13 @@
  *
  * Kernels:
  *   encode_bases_kernel      ASCII -> nt4 codes (HBM bound, 1 B in / 1 B out per base)
- *   poa_group_kernel<V>      persistent, one warp per read group: graph build, adaptive-banded
- *                            convex-gap DP (V=0 int32 lanes, V=2/4/8 packed int16x2 DPX), value
+ *   poa_group_kernel<T,WPL>  persistent, one TEAM of T lanes per read group (T = 16: two groups per
+ *                            warp): graph build, adaptive-banded convex-gap DP (WPL = 0 int32
+ *                            lanes, WPL = 4/6/8 packed int16x2 DPX words per lane), value
  *                            traceback, graph merge, heaviest-bundle consensus
  *   gather_consensus_kernel  per-group consensus regions -> one compact buffer
  */
 #include "poa_traceback.cuh"
-
-#ifndef MPOA_V2_BLOCKS
-#define MPOA_V2_BLOCKS 5
-#endif
-#ifndef MPOA_V0_BLOCKS
-#define MPOA_V0_BLOCKS 3
-#endif
-#ifndef MPOA_V4_BLOCKS
-#define MPOA_V4_BLOCKS 5
-#endif
 
 namespace mpoa {
 
@@ -65,131 +56,223 @@ __global__ void encode_bases_kernel(const uint8_t *__restrict__ ascii, uint8_t *
 /* the persistent kernel                                                                       */
 /* ------------------------------------------------------------------------------------------ */
 
-/* TRACE: the per-read / per-base trace outputs of the ABI (parity tests).  It is a compile-time
- * switch because the kernel's instruction footprint matters: the production instantiation is
- * ~370 SASS instructions smaller and measurably faster (resident warps share the instruction cache). */
-template <int V, bool TRACE>
-__device__ __forceinline__ int process_group(const KernelArgs &A, int slot, int g, int *ring, int4 *ring_info, int lane,
-                                             unsigned long long *st /* per-warp counters in shared memory, lane 0 only */) {
-    const int64_t r0 = A.group_read_off[g], r1 = A.group_read_off[g + 1];
-    if (r1 <= r0) return ST_EMPTY;
-    const int64_t gbase = A.read_off[r0];
-    int par = 0, N = 0, E = 0;
-    Slot S = make_slot(A, slot, par);
-    for (int64_t r = r0; r < r1; ++r) {
-        const int64_t b0 = A.read_off[r], b1 = A.read_off[r + 1];
-        const int len = (int)(b1 - b0);
-        const uint8_t *seq = A.codes + b0;
-        const int creator0 = (int)(b0 - gbase);
-        int32_t *tr_aln = nullptr, *tr_node = nullptr;
-        if constexpr (TRACE) { tr_aln = A.tr_aln + b0; tr_node = A.tr_node + b0; }
-        if constexpr (TRACE) {
-            if (lane == 0) { A.tr_score[r] = 0; A.tr_bits[r] = 0; A.tr_cells[r] = 0; }
-        }
-        if (N == 0) {
-            if (len <= 0) return ST_EMPTY;
-            if ((uint32_t)(len + 2) > A.L.ncap || (uint32_t)(len + 1) > A.L.ecap) return ST_RETRY;
-            init_graph<TRACE>(A, S, seq, len, creator0, lane);
-            N = len + 2; E = len + 1;
-            for (int t = lane; t < len; t += 32) {
-                if constexpr (TRACE) { tr_aln[t] = -1; tr_node[t] = creator0 + t; }
+/* per-team state of the group in flight (registers) */
+struct GroupState {
+    int g;               // group index, -1: none
+    int64_t r, r1;       // next read, end of the group's reads
+    int64_t gbase;       // first base of the group
+    int N, E, par;
+    long long t0;
+};
+
+/*
+ * One read of the group in flight of every team of the warp (lockstep, see Team): the first read
+ * becomes the chain graph, every other read is aligned (remain pass, banded DP, traceback) and
+ * merged.  `act`: this team has a read to process.  Returns ST_PENDING while the team's group
+ * goes on, a final status otherwise.
+ * TRACE: the per-read / per-base trace outputs of the ABI (parity tests).  It is a compile-time
+ * switch because the kernel's instruction footprint matters (resident warps share the
+ * instruction cache).
+ */
+template <int T, int WPL, bool TRACE>
+__device__ __forceinline__ int read_step(const KernelArgs &A, const Team<T> &tm, int slot, GroupState &G, bool act, int *ring, int4 *ring_info,
+                                         unsigned long long *st /* per-team counters in shared memory, lane 0 only */) {
+    const int lane = tm.tl;
+    int rc = ST_PENDING;
+    int64_t r = 0, b0 = 0;
+    int len = 0;
+    if (act) {
+        r = G.r++;
+        b0 = A.read_off[r];
+        len = (int)(A.read_off[r + 1] - b0);
+    }
+    const uint8_t *seq = A.codes + b0;
+    const int creator0 = (int)(b0 - G.gbase);
+    Slot S = make_slot(A, slot, G.par);
+    int32_t *tr_aln = nullptr, *tr_node = nullptr;
+    if constexpr (TRACE) {
+        tr_aln = A.tr_aln + b0; tr_node = A.tr_node + b0;
+        if (act && lane == 0) { A.tr_score[r] = 0; A.tr_bits[r] = 0; A.tr_cells[r] = 0; }
+    }
+    bool aln = false;                         // this team aligns a read in this step
+    if (act) {
+        if (G.N == 0) {                       // first read of the group (no cross-lane operation in here)
+            if (len <= 0) rc = ST_EMPTY;
+            else if ((uint32_t)(len + 2) > A.L.ncap || (uint32_t)(len + 1) > A.L.ecap) rc = ST_RETRY;
+            else {
+                init_graph<T, TRACE>(A, S, tm, seq, len, creator0);
+                G.N = len + 2; G.E = len + 1;
+                if constexpr (TRACE) {
+                    for (int t = lane; t < len; t += T) { tr_aln[t] = -1; tr_node[t] = creator0 + t; }
+                }
             }
-            continue;
+        } else if (len > 0) {
+            if ((uint32_t)len > A.L.qcap) rc = ST_RETRY;
+            else aln = true;
         }
-        if (len <= 0) continue;
-        if ((uint32_t)len > A.L.qcap) return ST_RETRY;
-        long long tk0 = clock64();
-        remain_pass(A, S, N, lane);
-        long long tk1 = clock64();
-        if (lane == 0) st[SI_T_PREP] += tk1 - tk0;
-        AlnState R;
-        int rc;
-        if constexpr (V == 0) rc = dp_align32(A, S, N, seq, len, ring, ring_info, lane, R);
-        else rc = dp_align16<V>(A, S, N, seq, len, reinterpret_cast<uint32_t *>(ring), lane, R);
-        if (rc != ST_OK) return rc;
-        tk0 = clock64();
-        if (lane == 0) {
-            st[SI_T_DP] += tk0 - tk1;
-            st[SI_CELLS] += R.cells; st[SI_INTOPS] += R.intops; st[SI_FULL] += R.full; st[SI_ALN] += 1;
-            st[R.bits == 16 ? SI_ALN16 : SI_ALN32] += 1; st[SI_TB] += R.tbbytes;
-            if constexpr (TRACE) { A.tr_score[r] = R.best_score; A.tr_bits[r] = R.bits; A.tr_cells[r] = (long long)R.cells; }
-        }
-        __syncwarp();
-        bool ok;
-        if constexpr (V == 0) ok = traceback<int32_t>(A, S, seq, len, R, lane, ring);
-        else ok = traceback<int16_t>(A, S, seq, len, R, lane, ring);
-        __syncwarp();
-        if (!ok) return ST_EMPTY;
-        tk1 = clock64();
-        if (lane == 0) st[SI_T_TB] += tk1 - tk0;
-        const int mrc = merge_read(A, S, par, N, E, seq, len, creator0, tr_aln, tr_node, lane);
-        if (mrc != ST_OK) return mrc;
-        S = make_slot(A, slot, par);
-        if (lane == 0) st[SI_T_MERGE] += clock64() - tk1;
     }
-    if (N <= 2) return ST_EMPTY;
-    const long long tc0 = clock64();
+    tm.sync();
+    if (!tm.wany(aln)) return rc;
+
+    long long tk0 = clock64();
+    remain_pass<T>(A, S, tm, G.N, aln);
+    long long tk1 = clock64();
+    if (aln && lane == 0) st[SI_T_PREP] += tk1 - tk0;
+    AlnState R;
+    int drc;
+    if constexpr (WPL == 0) drc = dp_align32(A, S, G.N, seq, len, ring, ring_info, lane, R);
+    else drc = dp_band16<T, WPL>(A, S, tm, G.N, seq, len, reinterpret_cast<uint32_t *>(ring), R, aln);
+    if (aln && drc != ST_OK) { rc = drc; aln = false; }
+    tk0 = clock64();
+    if (aln && lane == 0) {
+        st[SI_T_DP] += tk0 - tk1;
+        st[SI_CELLS] += R.cells; st[SI_INTOPS] += R.intops; st[SI_FULL] += R.full; st[SI_ALN] += 1;
+        st[R.bits == 16 ? SI_ALN16 : SI_ALN32] += 1; st[SI_TB] += R.tbbytes;
+        if constexpr (TRACE) { A.tr_score[r] = R.best_score; A.tr_bits[r] = R.bits; A.tr_cells[r] = (long long)R.cells; }
+    }
+    tm.sync();
+    if (!tm.wany(aln)) return rc;
+    bool ok;
+    if constexpr (WPL == 0) ok = traceback<int32_t, 0, T>(A, S, tm, seq, len, R, ring, aln);
+    else ok = traceback<int16_t, 2 * WPL, T>(A, S, tm, seq, len, R, ring, aln);
+    tm.sync();
+    if (aln && !ok) { rc = ST_EMPTY; aln = false; }
+    tk1 = clock64();
+    if (aln && lane == 0) st[SI_T_TB] += tk1 - tk0;
+    if (!tm.wany(aln)) return rc;
+    const int mrc = merge_read<T>(A, S, tm, G.par, G.N, G.E, seq, len, creator0, tr_aln, tr_node, aln);
+    if (aln && mrc != ST_OK) rc = mrc;
+    if (aln && lane == 0) st[SI_T_MERGE] += clock64() - tk1;
+    return rc;
+}
+
+/* after the last read: heaviest-bundle consensus into the group's region (`fin`: this team finishes a group) */
+template <int T>
+__device__ __forceinline__ int finish_group(const KernelArgs &A, const Team<T> &tm, int slot, const GroupState &G, bool fin, unsigned long long *st) {
     int clen = 0;
-    if (lane == 0) {
-        const int cap = (int)(A.cons_off[g + 1] - A.cons_off[g]);
-        clen = heaviest_bundle(A, S, N, A.cons + A.cons_off[g], cap);
+    const long long tc0 = clock64();
+    if (fin && tm.tl == 0 && G.N > 2) {       // one lane per team; no cross-lane operation
+        const Slot S = make_slot(A, slot, G.par);
+        const int cap = (int)(A.cons_off[G.g + 1] - A.cons_off[G.g]);
+        clen = heaviest_bundle(A, S, G.N, A.cons + A.cons_off[G.g], cap);
     }
-    clen = __shfl_sync(FULL, clen, 0);
-    __syncwarp();
+    clen = tm.shfl(clen, 0);
+    tm.sync();
+    if (!fin) return ST_PENDING;
+    if (G.N <= 2) return ST_EMPTY;
     if (clen < 0) return ST_RETRY;
-    if (lane == 0) { A.cons_len[g] = clen; st[SI_T_CONS] += clock64() - tc0; }
+    if (tm.tl == 0) { A.cons_len[G.g] = clen; st[SI_T_CONS] += clock64() - tc0; }
     return ST_OK;
 }
 
-template <int V>
-__host__ __device__ constexpr int variant_warp_words(int wcap) {
-    /* + 32 words: the warp's work counters (SI_COUNT x u64) */
-    return (V == 0 ? RING * 3 * wcap + RING * 4 : ring16_warp_words<(V == 0 ? 2 : V)>()) + 32;
+/* shared-memory words of one team: DP ring (also the traceback scratch) + its work counters (SI_COUNT x u64) */
+template <int T, int WPL>
+__host__ __device__ constexpr int team_words(int wcap) {
+    int w = WPL == 0 ? RING * 3 * wcap + RING * 4 : ring16_team_words<T, (WPL == 0 ? 2 : WPL)>();
+    if (w < tb_scratch_words<T>()) w = tb_scratch_words<T>();
+    return ((w + 3) & ~3) + 32;
 }
 
-template <int V, bool TRACE>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (V == 2 ? MPOA_V2_BLOCKS : V == 4 ? MPOA_V4_BLOCKS : V == 8 ? 3 : MPOA_V0_BLOCKS))
+#ifndef MPOA_MINB_16_4
+#define MPOA_MINB_16_4 4
+#endif
+#ifndef MPOA_MINB_16_6
+#define MPOA_MINB_16_6 3
+#endif
+#ifndef MPOA_MINB_32_4
+#define MPOA_MINB_32_4 5
+#endif
+#ifndef MPOA_MINB_32_2
+#define MPOA_MINB_32_2 5
+#endif
+#ifndef MPOA_MINB_32_8
+#define MPOA_MINB_32_8 3
+#endif
+#ifndef MPOA_MINB_32_0
+#define MPOA_MINB_32_0 3
+#endif
+template <int T, int WPL>
+__host__ __device__ constexpr int min_blocks() {
+    return WPL == 0 ? MPOA_MINB_32_0 : T == 16 ? (WPL <= 4 ? MPOA_MINB_16_4 : MPOA_MINB_16_6) : (WPL <= 2 ? MPOA_MINB_32_2 : WPL <= 4 ? MPOA_MINB_32_4 : MPOA_MINB_32_8);
+}
+
+/*
+ * Persistent kernel: every TEAM (T lanes) pulls read groups from the launch's queue (heaviest
+ * first) and carries each one from its first read to the consensus.  The loop is flat -- one iteration = one read of every team's group -- and the
+ * teams of a warp run it in lockstep (see Team): a team without work idles by predicate until the
+ * other one is done as well.
+ */
+template <int T, int WPL, bool TRACE>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (min_blocks<T, WPL>()))
 poa_group_kernel(const __grid_constant__ KernelArgs A) {
+    static_assert(WPL != 0 || T == 32, "int32 lanes use the whole warp");
     extern __shared__ __align__(16) int smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int per_warp = variant_warp_words<V>(A.wcap);
-    int *ring = smem + warp * per_warp;
-    int4 *ring_info = reinterpret_cast<int4 *>(ring + per_warp - 32 - RING * 4);   // int32 variant only
-    /* work counters of the group in flight: shared memory, touched by lane 0 only (they used to sit
-     * in 26 registers across the DP row loop) */
-    unsigned long long *gst = reinterpret_cast<unsigned long long *>(ring + per_warp - 32);
+    constexpr int TPW = 32 / T;                       // teams per warp
+    const int warp = threadIdx.x >> 5;
+    /* the lane index goes through shared memory once: ptxas otherwise re-derives it from the
+     * thread-id register (S2R + LOP3) all over the row loop instead of keeping it in a register */
+    int wl = threadIdx.x & 31;
+    {
+        volatile int *lane_box = smem + (blockDim.x >> 5) * (32 / T) * team_words<T, WPL>(A.wcap);
+        lane_box[threadIdx.x] = wl;
+        wl = lane_box[threadIdx.x];
+    }
+    const Team<T> tm(wl);
+    const int team = warp * TPW + wl / T;
+    const int per_team = team_words<T, WPL>(A.wcap);
+    int *ring = smem + team * per_team;
+    int4 *ring_info = reinterpret_cast<int4 *>(ring + RING * 3 * A.wcap);   // int32 variant only
+    /* work counters of the group in flight: shared memory, touched by team lane 0 only */
+    unsigned long long *gst = reinterpret_cast<unsigned long long *>(ring + per_team - 32);
     static_assert(SI_COUNT <= 16, "counter block");
-    const int slot = blockIdx.x * (blockDim.x >> 5) + warp;
-    int src = -1;   // -1: own queue, k >= 0: steal queue k
+    const int slot = blockIdx.x * (blockDim.x >> 5) * TPW + team;
+    GroupState G;
+    G.g = -1; G.r = G.r1 = 0; G.gbase = 0; G.N = G.E = G.par = 0; G.t0 = 0;
+    bool dry = false;        // the queue has nothing left for this team
     for (;;) {
-        int qi = 0, g = -1;
-        for (;;) {
-            int *head = src < 0 ? A.queue_head : A.steal_head[src];
-            const int n = src < 0 ? A.n_queue : A.steal_n[src];
-            if (lane == 0) qi = atomicAdd(head, 1);
-            qi = __shfl_sync(FULL, qi, 0);
-            if (qi < n) { g = (src < 0 ? A.queue : A.steal_queue[src])[qi]; break; }
-            if (++src >= A.n_steal) break;
-        }
-        if (g < 0) break;
-        if (lane == 0) {
+        if (G.g < 0 && !dry) {                        // per team; team lane 0 only, no cross-lane operation
+            int g = -1;
+            if (tm.tl == 0) {
+                const int qi = atomicAdd(A.queue_head, 1);
+                if (qi < A.n_queue) g = A.queue[qi];
+                if (g >= 0) {
 #pragma unroll
-            for (int k = 0; k < SI_COUNT; ++k) gst[k] = 0;
-        }
-        const long long tg0 = clock64();
-        int rc;
-        if constexpr (V == 0) rc = process_group<V, TRACE>(A, slot, g, ring, ring_info, lane, gst);
-        else rc = process_group<V, TRACE>(A, slot, g, ring, nullptr, lane, gst);
-        if (lane == 0) {
-            A.status[g] = rc;
-            if (rc != ST_OK) A.cons_len[g] = 0;
-            if (rc != ST_RETRY && rc != ST_RETRY_WIDE && rc != ST_RETRY_32) {
-                gst[SI_T_BUSY] += clock64() - tg0;
-                for (int k = 0; k < SI_COUNT; ++k)
-                    if (gst[k]) atomicAdd(A.stats + k, gst[k]);
+                    for (int k = 0; k < SI_COUNT; ++k) gst[k] = 0;
+                }
             }
+            G.g = g;
         }
-        __syncwarp();
+        G.g = tm.shfl(G.g, 0);
+        if (G.g < 0) dry = true;
+        else if (G.N == 0 && G.r == G.r1) {           // a group that was just fetched
+            G.r = A.group_read_off[G.g]; G.r1 = A.group_read_off[G.g + 1];
+            G.par = 0; G.E = 0;
+            G.t0 = clock64();
+            if (G.r1 > G.r) G.gbase = A.read_off[G.r];
+        }
+        if (!tm.wany(G.g >= 0)) break;
+        const bool act = G.g >= 0 && G.r < G.r1;
+        int rc = read_step<T, WPL, TRACE>(A, tm, slot, G, act, ring, ring_info, gst);
+        if (G.g >= 0 && !act) rc = ST_EMPTY;          // a group without reads
+        const bool fin = G.g >= 0 && rc == ST_PENDING && G.r == G.r1;
+        if (tm.wany(fin)) {
+            const int frc = finish_group<T>(A, tm, slot, G, fin, gst);
+            if (fin) rc = frc;
+        }
+        if (G.g >= 0 && rc != ST_PENDING) {
+            if (tm.tl == 0) {
+                const bool retry = rc == ST_RETRY || rc == ST_RETRY_WIDE || rc == ST_RETRY_32;
+                A.status[G.g] = retry ? (rc | (A.level << 8)) : rc;
+                if (rc != ST_OK) A.cons_len[G.g] = 0;
+                if (!retry) {
+                    gst[SI_T_BUSY] += clock64() - G.t0;
+                    for (int k = 0; k < SI_COUNT; ++k)
+                        if (gst[k]) atomicAdd(A.stats + k, gst[k]);
+                }
+            }
+            G.g = -1; G.N = 0; G.r = G.r1 = 0;
+        }
+        tm.sync();
     }
 }
 
@@ -252,47 +335,45 @@ cudaError_t launch_gather(const uint8_t *cons, const int64_t *region_off, const 
     return cudaGetLastError();
 }
 
-template <int V>
+template <int T, int WPL>
 static const void *variant_fn(bool trace) {
-    return trace ? reinterpret_cast<const void *>(&poa_group_kernel<V, true>) : reinterpret_cast<const void *>(&poa_group_kernel<V, false>);
+    return trace ? reinterpret_cast<const void *>(&poa_group_kernel<T, WPL, true>) : reinterpret_cast<const void *>(&poa_group_kernel<T, WPL, false>);
 }
 
-static const void *kernel_of(int variant, bool trace) {
-    switch (variant) {
-        case 2: return variant_fn<2>(trace);
-        case 4: return variant_fn<4>(trace);
-        case 8: return variant_fn<8>(trace);
-        default: return variant_fn<0>(trace);
-    }
+/* the instantiated kernel variants: (team size, words per lane) */
+#define MPOA_FOR_VARIANTS(X) X(32, 2) X(32, 4) X(32, 8) X(32, 0)
+
+static const void *kernel_of(int code, bool trace) {
+#define X(T, W) if (code == variant_code(T, W)) return variant_fn<T, W>(trace);
+    MPOA_FOR_VARIANTS(X)
+#undef X
+    return nullptr;
 }
 
-/* band capacity (cells per row) of a variant; variant 0 takes any wcap */
-int variant_wcap(int variant, int wcap) { return variant == 0 ? wcap : 64 * variant; }
+bool variant_exists(int code) { return kernel_of(code, false) != nullptr; }
 
-size_t poa_smem_bytes(int variant, int wcap, int warps_per_block) {
-    int words;
-    switch (variant) {
-        case 2: words = variant_warp_words<2>(wcap); break;
-        case 4: words = variant_warp_words<4>(wcap); break;
-        case 8: words = variant_warp_words<8>(wcap); break;
-        default: words = variant_warp_words<0>(wcap); break;
-    }
-    return (size_t)warps_per_block * words * sizeof(int);
+size_t poa_smem_bytes(int code, int wcap, int warps_per_block) {
+#define X(T, W) if (code == variant_code(T, W)) return ((size_t)warps_per_block * (32 / T) * team_words<T, W>(wcap) + warps_per_block * 32) * sizeof(int);
+    MPOA_FOR_VARIANTS(X)
+#undef X
+    return 0;
 }
 
-cudaError_t launch_poa(int variant, const KernelArgs &A, int n_blocks, int warps_per_block, cudaStream_t stream) {
-    const size_t smem = poa_smem_bytes(variant, A.wcap, warps_per_block);
-    const void *fn = kernel_of(variant, A.tr_aln != nullptr);   // all five trace arrays are set together
+cudaError_t launch_poa(int code, const KernelArgs &A, int n_blocks, int warps_per_block, cudaStream_t stream) {
+    const size_t smem = poa_smem_bytes(code, A.wcap, warps_per_block);
+    const void *fn = kernel_of(code, A.tr_aln != nullptr);   // all five trace arrays are set together
+    if (!fn) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     void *args[] = {const_cast<KernelArgs *>(&A)};
     return cudaLaunchKernel(fn, dim3(n_blocks), dim3(warps_per_block * 32), args, smem, stream);
 }
 
-int poa_max_blocks_per_sm(int variant, int wcap, int warps_per_block) {
+int poa_max_blocks_per_sm(int code, int wcap, int warps_per_block) {
     int nb = 0;
-    const size_t smem = poa_smem_bytes(variant, wcap, warps_per_block);
-    const void *fn = kernel_of(variant, false);
+    const size_t smem = poa_smem_bytes(code, wcap, warps_per_block);
+    const void *fn = kernel_of(code, false);
+    if (!fn) return 0;
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, warps_per_block * 32, smem) != cudaSuccess) return 0;
     return nb;

@@ -1,16 +1,18 @@
 """Developer tool: static view of the packed DP row loop in the built library (no GPU needed).
 Prints the SASS between the row-loop head (the REDUX.OR metadata broadcast) and its back branch,
-with an opcode histogram.  usage: python scripts/sass_loop.py [variant=4] [-v]"""
+with an opcode histogram.  usage: python scripts/sass_loop.py [WPL=4] [T=32] [-v]"""
 import collections
 import re
 import subprocess
 import sys
 
-V = sys.argv[1] if len(sys.argv) > 1 and sys.argv[1].isdigit() else "4"
+args = [a for a in sys.argv[1:] if a.isdigit()]
+V = args[0] if args else "4"
+TT = args[1] if len(args) > 1 else "32"
 verbose = "-v" in sys.argv
 txt = subprocess.run(["cuobjdump", "-sass", "mandalorion_b200/libmandalorion_poa.so"], capture_output=True, text=True).stdout
 funcs = re.split(r"\n\s*Function : ", txt)
-body = next(f for f in funcs if f.startswith("_ZN4mpoa16poa_group_kernelILi%sELb0EEE" % V))
+body = next(f for f in funcs if f.startswith("_ZN4mpoa16poa_group_kernelILi%sELi%sELb0EEE" % (TT, V)))
 ins = []
 for ln in body.splitlines():
     m = re.match(r"\s*/\*([0-9a-f]{4,6})\*/\s+(.*?);", ln)
@@ -30,7 +32,7 @@ for k, (a, s) in enumerate(ins):
         best = (addr2k[t], k)
 first, back = best
 loop = ins[first:back + 1]
-print("kernel V=%s: %d SASS instructions in the function, row loop spans %d (0x%x..0x%x)" % (V, len(ins), len(loop), loop[0][0], loop[-1][0]))
+print("kernel T=" + TT + " WPL=%s: %d SASS instructions in the function, row loop spans %d (0x%x..0x%x)" % (V, len(ins), len(loop), loop[0][0], loop[-1][0]))
 hist = collections.Counter(re.sub(r"^@!?U?P\d+\s+", "", s).split()[0] for a, s in loop)
 print(" ".join("%s:%d" % kv for kv in hist.most_common()))
 if verbose:
