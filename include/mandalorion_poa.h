@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MPOA_ABI_VERSION 1
+#define MPOA_ABI_VERSION 2
 
 /* error codes (negative return values) */
 #define MPOA_OK          0
@@ -92,7 +92,12 @@ typedef struct mpoa_stats {
     int64_t n_kernel_launches; /* kernels of this library launched by the call           */
     int64_t phase_cycles[6];  /* SM cycles summed over warps: graph-prep, DP, traceback,
                                  merge, consensus, total busy                            */
-    int64_t reserved[2];
+    int64_t n_seed_groups;   /* groups flagged MPOA_FLAG_SEED (the reference would pass -S) */
+    int64_t n_seed_applied;  /* ... of which were aligned with minimizer seeding; the rest
+                                ran the unseeded algorithm (see mpoa_seed_policy below)     */
+    int64_t n_too_big_groups;/* groups that ended as MPOA_GROUP_TOO_BIG                    */
+    int64_t max_band_width;  /* widest band row of the batch, cells (oracle only; 0 here)  */
+    int64_t reserved[4];
 } mpoa_stats;
 
 /*
@@ -163,6 +168,20 @@ int  mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups,
 int  mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats);
 int  mpoa_batch_fetch(mpoa_ctx *ctx, int64_t *cons_off, uint8_t *cons_buf, int64_t cons_cap,
                       int32_t *group_status, mpoa_trace *trace);
+
+/*
+ * Orientation of every read of a group against the group's FIRST read -- what the reference
+ * obtains from mappy before it writes the abpoa input (utils/SpliceDefineConsensus.py:895,
+ * :900-907: mp.Aligner(seq=first, preset='map-ont'), one output record per PRIMARY hit,
+ * reverse-complemented when hit.strand == -1, reads without a primary hit dropped).
+ *   hit_count[n_reads]     (out) primary hits of the read: 0 (dropped), 1, or 2 (written twice)
+ *   hit_strand[2*n_reads]  (out) +1 / -1 per hit, best chain first
+ * Host code (minimizer sketch k=15 w=10 + colinear chaining, the seed-chain stage of minimap2's
+ * map-ont; no base-level extension), n_threads worker threads over groups; needs no context
+ * and no GPU.  The Python layer uses mappy itself whenever it is importable.
+ */
+int  mpoa_orient_batch(int64_t n_groups, const int64_t *group_read_off, const int64_t *read_base_off,
+                       const uint8_t *bases, int32_t n_threads, int8_t *hit_count, int8_t *hit_strand);
 
 #ifdef __cplusplus
 }

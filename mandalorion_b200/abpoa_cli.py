@@ -52,12 +52,16 @@ def parse_args(argv):
 
 def main(argv=None):
     from .poa import PoaContext
-    params, _seed, path = parse_args(sys.argv[1:] if argv is None else argv)
+    params, seed, path = parse_args(sys.argv[1:] if argv is None else argv)
     reads = read_fasta(path)
     if not reads:
         return 0
+    if seed:
+        # abpoa -S = minimizer-seeded, windowed alignment (reference :919, median read length >= 8000);
+        # this library aligns every group unseeded and says so (stderr goes to abpoa.messages in the reference)
+        sys.stderr.write("abpoa-b200: -S accepted, but the group is aligned WITHOUT minimizer seeding\n")
     with PoaContext(0, params) as ctx:
-        out = ctx.consensus_batch([reads])
+        out = ctx.consensus_batch([reads], flags=[1 if seed else 0])
     if out["status"][0] == 0 and out["cons"][0]:
         sys.stdout.write(">Consensus_sequence\n%s\n" % out["cons"][0].decode())
     return 0

@@ -12,7 +12,8 @@ workers; the GPU wants thousands of groups per call.  So the step is split in tw
 
   prepare_group()   everything determine_consensus() does BEFORE abpoa (lines :878-:915):
                     the np.random.choice subsample/permutation (same call, same RNG
-                    consumption), orientation of every read against the first one, the
+                    consumption), orientation of every read against the first one (mappy when
+                    importable, else batched through the library's mpoa_orient_batch), the
                     "<= 2 usable reads" bypass and the -S decision.  Returns a PendingGroup.
   ConsensusBatcher  collects PendingGroups, runs them through PoaContext.consensus_batch()
                     (the C ABI, CUDA) and applies the reference's post-processing
@@ -21,11 +22,20 @@ workers; the GPU wants thousands of groups per call.  So the step is split in tw
 determine_consensus() below is the one-group convenience with the reference's signature.
 Nothing in this module computes an alignment on the CPU.
 """
+import warnings
 from dataclasses import dataclass, field
 
 import numpy as np
 
 from .poa import PoaContext, pack_groups
+
+class SeedingNotApplied(UserWarning):
+    """groups the reference would run with `abpoa -S` were aligned without minimizer seeding"""
+
+
+class GroupTooBig(UserWarning):
+    """a group outgrew every device capacity and fell back to its first read"""
+
 
 _COMP = bytes.maketrans(b"ACGTUNacgtun", b"TGCAANtgcaan")
 
@@ -52,42 +62,38 @@ class MappyOrienter:
         return [h.strand for h in self._al.map(sequence) if h.is_primary]
 
 
-class KmerOrienter:
-    """Stand-in when mappy is absent (it is not installable in the build image): a k-mer strand
-    vote against the first read.  One 'primary hit' on the winning strand, none when neither
-    strand shares enough k-mers (the reference drops such reads, :902-907).  This is NOT
-    minimap2; it reproduces its strand call for reads of one isoform.  SURVEY.md section 8f
-    ranks the exact orientation step as the next row to build."""
+def mappy_available():
+    try:
+        import mappy  # noqa: F401
+        return True
+    except ImportError:
+        return False
 
-    K = 13
+
+def native_hits(read_groups, n_threads=None):
+    """Primary-hit strands of every read of every group against the group's first read, computed by
+    the library's own seed-chain stage of minimap2's map-ont (C ABI mpoa_orient_batch, C++ threads;
+    csrc/orient.cpp) in ONE call.  read_groups: list of lists of str.  Returns, per group, a list
+    (one entry per read) of strand lists like MappyOrienter.hits()."""
+    from .poa import orient_batch
+    packed = pack_groups(read_groups)
+    cnt, strand = orient_batch(packed, n_threads=n_threads)
+    out, r = [], 0
+    for reads in read_groups:
+        out.append([[int(strand[r + i, h]) for h in range(int(cnt[r + i]))] for i in range(len(reads))])
+        r += len(reads)
+    return out
+
+
+class NativeOrienter:
+    """MappyOrienter's interface on top of the library's own seed-chain stage (one call per read:
+    for single groups and test doubles; the batched path is orient_pending())."""
 
     def __init__(self, first):
-        self._set = self._kmers(first)
-
-    @classmethod
-    def _kmers(cls, s):
-        k = cls.K
-        return {s[i:i + k] for i in range(0, max(0, len(s) - k + 1))}
-
-    def _score(self, s):
-        k = self.K
-        st = self._set
-        return sum(1 for i in range(0, max(0, len(s) - k + 1), 3) if s[i:i + k] in st)
+        self._first = first
 
     def hits(self, sequence):
-        f = self._score(sequence)
-        r = self._score(revcomp(sequence))
-        need = max(2, (len(sequence) // 3) // 50)
-        if max(f, r) < need:
-            return []
-        return [1 if f >= r else -1]
-
-
-def default_orienter(first):
-    try:
-        return MappyOrienter(first)
-    except ImportError:
-        return KmerOrienter(first)
+        return native_hits([[self._first, sequence]])[0][1]
 
 
 # ------------------------------------------------------------------------------------------
@@ -97,20 +103,43 @@ def default_orienter(first):
 @dataclass
 class PendingGroup:
     names: list                    # ALL read names of the isoform (reference :880-882, :931)
-    sequences: list                # oriented reads in abpoa's file order (reference :906-907)
+    sequences: list                # oriented reads in abpoa's file order (reference :906-907); None until oriented
     seq_lengths: list              # lengths of every subsampled read, dropped ones included (:901)
     bypass: bool                   # len(sequences) <= 2 -> consensus = sequences[0] (:911-912)
     seed: bool                     # median length >= 8000 -> the reference adds -S (:915-919)
     tag: object = None
     consensus: str = field(default=None)
+    subsample: list = field(default=None)   # [(name, seq)] in subsample order while orientation is pending
 
 
-def prepare_group(reads, orienter_factory=default_orienter, rng=None, tag=None):
+def _apply_hits(pg, hits_per_read):
+    """reference :900-907 for one group: one output record per primary hit, reverse-complemented
+    (cumulatively, like the reference's in-place `sequence = mp.revcomp(sequence)`) on '-' hits."""
+    sequences = []
+    for (read, sequence), hits in zip(pg.subsample, hits_per_read):
+        for strand in hits:
+            if strand == -1:
+                sequence = revcomp(sequence)
+            sequences.append(sequence)
+    pg.sequences = sequences
+    pg.subsample = None
+    pg.bypass = len(sequences) <= 2
+    pg.seed = (not pg.bypass) and float(np.median(pg.seq_lengths)) >= 8000
+    if pg.bypass:
+        # reference :912 -- IndexError when nothing mapped, like the reference
+        pg.consensus = sequences[0]
+
+
+def prepare_group(reads, orienter_factory=None, rng=None, tag=None):
     """reads: [(name, seq), ...] exactly as define_start_end_sites() yields them.
 
     Consumes the NumPy RNG exactly like the reference: one
     np.random.choice(np.arange(0, n), min(n, 100), replace=False) on the GLOBAL legacy RNG
-    (or on `rng` when a RandomState is passed, for tests)."""
+    (or on `rng` when a RandomState is passed, for tests).
+
+    Orientation: `orienter_factory(first)` when given; else mappy when it is importable (the
+    reference's own calls); else the group is returned with orientation PENDING and
+    ConsensusBatcher.flush() / orient_pending() orients all such groups in one native call."""
     fasta_reads = []
     names = []
     for read, seq in reads:
@@ -120,23 +149,25 @@ def prepare_group(reads, orienter_factory=default_orienter, rng=None, tag=None):
     indeces = choice(np.arange(0, len(fasta_reads)), min(len(fasta_reads), 100), replace=False)
     subsample_fasta_reads = [fasta_reads[index] for index in indeces]
     first = subsample_fasta_reads[0][1]
-    sequences = []
-    seq_lengths = []
-    orienter = orienter_factory(first)
-    for read, sequence in subsample_fasta_reads:
-        seq_lengths.append(len(sequence))
-        # the reference loop re-reverses `sequence` in place for every '-' primary hit
-        for strand in orienter.hits(sequence):
-            if strand == -1:
-                sequence = revcomp(sequence)
-            sequences.append(sequence)
-    bypass = len(sequences) <= 2
-    seed = (not bypass) and float(np.median(seq_lengths)) >= 8000
-    pg = PendingGroup(names=names, sequences=sequences, seq_lengths=seq_lengths, bypass=bypass, seed=seed, tag=tag)
-    if bypass:
-        # reference :912 -- IndexError when nothing mapped, like the reference
-        pg.consensus = sequences[0]
+    seq_lengths = [len(sequence) for read, sequence in subsample_fasta_reads]
+    pg = PendingGroup(names=names, sequences=None, seq_lengths=seq_lengths, bypass=None, seed=None, tag=tag,
+                      subsample=subsample_fasta_reads)
+    if orienter_factory is None and mappy_available():
+        orienter_factory = MappyOrienter
+    if orienter_factory is not None:
+        orienter = orienter_factory(first)
+        _apply_hits(pg, [orienter.hits(sequence) for read, sequence in subsample_fasta_reads])
     return pg
+
+
+def orient_pending(pgs, n_threads=None):
+    """Orients every group of `pgs` whose orientation is still pending, in one native call."""
+    todo = [pg for pg in pgs if pg.sequences is None]
+    if not todo:
+        return
+    hits = native_hits([[sequence for read, sequence in pg.subsample] for pg in todo], n_threads=n_threads)
+    for pg, h in zip(todo, hits):
+        _apply_hits(pg, h)
 
 
 class ConsensusBatcher:
@@ -160,7 +191,9 @@ class ConsensusBatcher:
         return pg
 
     def flush(self):
-        """Runs every non-bypassed pending group; fills .consensus; returns the groups in add() order."""
+        """Orients what is still pending, runs every non-bypassed group on the GPU; fills .consensus;
+        returns the groups in add() order."""
+        orient_pending(self._pending)
         todo = [pg for pg in self._pending if not pg.bypass and pg.consensus is None]
         start = 0
         while start < len(todo):
@@ -173,8 +206,18 @@ class ConsensusBatcher:
             flags = np.array([1 if pg.seed else 0 for pg in chunk], dtype=np.uint8)
             ctx = self.ctx
             ctx.upload(gro, rbo, bases, flags)
-            self.stats.append(ctx.run())
+            st = ctx.run()
+            self.stats.append(st)
             out = ctx.fetch()
+            n_unseeded = st.get("n_seed_groups", 0) - st.get("n_seed_applied", 0)
+            if n_unseeded > 0:
+                warnings.warn(f"{n_unseeded} group(s) with median read length >= 8000: the reference runs `abpoa -S` "
+                              "(minimizer-seeded windows) for them, this library aligned them unseeded "
+                              "(include/mandalorion_poa.h, MPOA_FLAG_SEED)", SeedingNotApplied, stacklevel=2)
+            if st.get("n_too_big_groups", 0) > 0:
+                warnings.warn(f"{st['n_too_big_groups']} group(s) outgrew the device capacities (MPOA_GROUP_TOO_BIG): "
+                              "their consensus falls back to the first read, which is NOT what abpoa would print",
+                              GroupTooBig, stacklevel=2)
             for pg, cons, status in zip(chunk, out["cons"], out["status"]):
                 consensus_sequence = cons.decode() if status == 0 else ""
                 if not consensus_sequence:                    # reference :924-925
@@ -185,12 +228,13 @@ class ConsensusBatcher:
         return done
 
 
-def determine_consensus(reads, root=None, abpoa=None, ctx=None, orienter_factory=default_orienter, rng=None):
+def determine_consensus(reads, root=None, abpoa=None, ctx=None, orienter_factory=None, rng=None):
     """Drop-in for utils/SpliceDefineConsensus.determine_consensus (reference :876-931).
 
     `root` (temp-file prefix) and `abpoa` (binary path) are accepted for signature
     compatibility and unused: no file is written and no process is spawned."""
     pg = prepare_group(reads, orienter_factory=orienter_factory, rng=rng)
+    orient_pending([pg])
     if not pg.bypass:
         b = ConsensusBatcher(ctx)
         b.add(pg)
@@ -202,13 +246,15 @@ def determine_consensus(reads, root=None, abpoa=None, ctx=None, orienter_factory
 # module-D dispatch (reference defineIsoforms.py:87-91 and :155-166)
 # ------------------------------------------------------------------------------------------
 
-def consensus_for_loci(loci_seqdicts, ctx=None, orienter_factory=default_orienter, rng=None):
+def consensus_for_loci(loci_seqdicts, ctx=None, orienter_factory=None, rng=None):
     """loci_seqdicts: iterable of (root, seqDict) in the reference's locus order, seqDict being
     what define_start_end_sites() returned for that locus.  Returns {root: IsoData} with
     IsoData[isoform] = [consensus, names] -- the structure process_locus() returns.
 
-    Groups are prepared in the reference's order (locus order, then dict order), so a
-    seeded global NumPy RNG is consumed identically, then ALL loci go to the GPU in one batch."""
+    Groups are prepared in the reference's order (locus order, then dict order) on ONE RNG stream,
+    then ALL loci go to the GPU in one batch.  NB the reference forks one worker per locus
+    (defineIsoforms.py:130), each starting from the parent's RNG state at fork time: to reproduce
+    ITS subsample order, prepare every locus in such a worker and use finish_prepared()."""
     batcher = ConsensusBatcher(ctx)
     results = {}
     for root, seq_dict in loci_seqdicts:

@@ -69,6 +69,7 @@ struct mpoa_ctx {
     /* uploaded batch */
     int64_t n_groups = 0, n_reads = 0, n_bases = 0;
     std::vector<int64_t> h_gro, h_rbo;
+    std::vector<uint8_t> h_flags;              // MPOA_FLAG_* per group (empty: none set)
     std::vector<GroupInfo> ginfo;
     uint8_t *d_codes = nullptr;
     int64_t *d_rbo = nullptr, *d_gro = nullptr, *d_region_off = nullptr;
@@ -210,7 +211,6 @@ extern "C" int mpoa_measure_int_peak(mpoa_ctx *ctx, double *warp_instr_per_sec) 
 
 extern "C" int mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups, const int64_t *group_read_off,
                                  const int64_t *read_base_off, const uint8_t *bases, const uint8_t *group_flags) {
-    (void)group_flags;  // MPOA_FLAG_SEED: the unseeded alignment is run for every group (scope)
     if (!ctx || n_groups < 0) return MPOA_EINVAL;
     if (n_groups > 0 && (!group_read_off || !read_base_off)) { ctx->err = "null offsets"; return MPOA_EINVAL; }
     CK(cudaSetDevice(ctx->dev));
@@ -237,6 +237,7 @@ extern "C" int mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups, const int64_t 
         ctx->err = msg;
         return (int)MPOA_EINVAL;
     };
+    if (group_flags) ctx->h_flags.assign(group_flags, group_flags + n_groups); else ctx->h_flags.clear();
     ctx->h_gro.assign(group_read_off, group_read_off + n_groups + 1);
     ctx->h_rbo.assign(read_base_off, read_base_off + n_reads + 1);
     ctx->ginfo.resize(n_groups);
@@ -523,16 +524,16 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
     std::vector<int32_t> dstat(ng);
     for (int round = 0; round < 12 && !pending.empty(); ++round) {
         /* one launch per level.  A level with fewer groups than the GPU holds teams is folded into
-         * the next wider level of the same lane family when there is one (every group runs correctly
-         * in any level at least as wide as its own); what stays small runs beside the big launches
-         * (run_round) */
+         * the next wider level of the same lane family when that one fills the GPU (every group runs
+         * correctly in any level at least as wide as its own); what stays small runs beside the big
+         * launches (run_round) */
         std::vector<std::vector<int32_t>> bins(kNumLevels);
         for (int32_t g : pending) bins[ctx->ginfo[g].level].push_back(g);
         const size_t min_groups = (size_t)ctx->n_sm * 16;
         for (int a = 0; a < kNumLevels; ++a) {
             if (bins[a].empty() || bins[a].size() >= min_groups) continue;
             for (int o = a + 1; o < kNumLevels; ++o)
-                if (!bins[o].empty() && (kLevels[o].WPL == 0) == (kLevels[a].WPL == 0)) {
+                if (bins[o].size() >= min_groups && (kLevels[o].WPL == 0) == (kLevels[a].WPL == 0)) {
                     bins[o].insert(bins[o].end(), bins[a].begin(), bins[a].end());
                     bins[a].clear();
                     break;
@@ -626,6 +627,11 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
     st.tb_bytes = (int64_t)hs[SI_TB];
     for (int k = 0; k < 6; ++k) st.phase_cycles[k] = (int64_t)hs[SI_T_PREP + k];
     st.n_kernel_launches = n_launch;
+    /* groups the reference would have run with `abpoa -S` (median read length >= 8000): this library
+     * aligns them WITHOUT minimizer seeding -- reported, never hidden (include/mandalorion_poa.h) */
+    for (uint8_t f : ctx->h_flags) st.n_seed_groups += (f & MPOA_FLAG_SEED) ? 1 : 0;
+    st.n_seed_applied = 0;
+    for (int64_t g = 0; g < ng; ++g) st.n_too_big_groups += ctx->h_status[g] == ST_TOO_BIG ? 1 : 0;
     ctx->last = st;
     ctx->ran = true;
     if (stats) *stats = st;

@@ -35,7 +35,8 @@ class _Stats(C.Structure):
                 ("n_align_i16", C.c_int64), ("n_align_i32", C.c_int64), ("tb_bytes", C.c_int64),
                 ("n_retry_groups", C.c_int64), ("kernel_ms", C.c_double), ("h2d_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("n_kernel_launches", C.c_int64), ("phase_cycles", C.c_int64 * 6),
-                ("reserved", C.c_int64 * 2)]
+                ("n_seed_groups", C.c_int64), ("n_seed_applied", C.c_int64), ("n_too_big_groups", C.c_int64),
+                ("max_band_width", C.c_int64), ("reserved", C.c_int64 * 4)]
 
 
 class _Trace(C.Structure):
@@ -64,7 +65,7 @@ _lib = None
 # every symbol include/mandalorion_poa.h declares
 ABI_SYMBOLS = ("mpoa_abi_version", "mpoa_default_params", "mpoa_create", "mpoa_destroy", "mpoa_last_error",
                "mpoa_set_stream", "mpoa_set_trace", "mpoa_measure_int_peak", "mpoa_consensus_batch", "mpoa_batch_upload", "mpoa_batch_run",
-               "mpoa_batch_fetch")
+               "mpoa_batch_fetch", "mpoa_orient_batch")
 
 
 def _load():
@@ -88,6 +89,7 @@ def _load():
         lib.mpoa_batch_run.argtypes = [C.c_void_p, C.c_void_p]
         lib.mpoa_batch_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         lib.mpoa_consensus_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6 + [C.c_int64] + [C.c_void_p] * 3
+        lib.mpoa_orient_batch.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -111,6 +113,22 @@ def pack_groups(groups):
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def orient_batch(packed, n_threads=None):
+    """Primary-hit strands of every read against the first read of its group (C ABI
+    mpoa_orient_batch; reference utils/SpliceDefineConsensus.py:895, :900-907).
+    Returns (hit_count int8[n_reads], hit_strand int8[n_reads, 2]).  Host code: needs no GPU."""
+    lib = _load()
+    gro, rbo, bases = [np.ascontiguousarray(a, dtype=t) for a, t in zip(packed, (np.int64, np.int64, np.uint8))]
+    nr = len(rbo) - 1
+    cnt = np.zeros(max(nr, 1), dtype=np.int8)
+    strand = np.zeros((max(nr, 1), 2), dtype=np.int8)
+    rc = lib.mpoa_orient_batch(len(gro) - 1, _ptr(gro), _ptr(rbo), _ptr(bases), int(n_threads or os.cpu_count() or 1),
+                               _ptr(cnt), _ptr(strand))
+    if rc != 0:
+        raise PoaError(f"mpoa_orient_batch failed with {rc}")
+    return cnt[:nr], strand[:nr]
 
 
 class PoaContext:
@@ -174,6 +192,8 @@ class PoaContext:
 
     # ---- three-stage interface (inputs stay resident in HBM between run() calls) ----
     def upload(self, gro, rbo, bases, flags=None):
+        if flags is not None:
+            flags = np.ascontiguousarray(flags, dtype=np.uint8)
         gro = np.ascontiguousarray(gro, dtype=np.int64)
         rbo = np.ascontiguousarray(rbo, dtype=np.int64)
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
@@ -208,13 +228,15 @@ class PoaContext:
         return dict(cons=cons, status=status, cons_off=cons_off, trace=arrs)
 
     # ---- the one-call interface ----
-    def consensus_batch(self, groups=None, packed=None, trace=False):
-        """groups: list of lists of reads (str/bytes), aligned in the given order.
-        Returns dict(cons=[bytes], status=int32[], stats=dict, trace=dict|None)."""
+    def consensus_batch(self, groups=None, packed=None, trace=False, flags=None):
+        """groups: list of lists of reads (str/bytes), aligned in the given order; flags: MPOA_FLAG_* per
+        group.  Returns dict(cons=[bytes], status=int32[], stats=dict, trace=dict|None)."""
         gro, rbo, bases = packed if packed is not None else pack_groups(groups)
+        if flags is not None:
+            flags = np.ascontiguousarray(flags, dtype=np.uint8)
         self.set_trace(trace)
         try:
-            self.upload(gro, rbo, bases)
+            self.upload(gro, rbo, bases, flags)
             stats = self.run()
             out = self.fetch(trace=trace)
         finally:

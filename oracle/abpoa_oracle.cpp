@@ -606,7 +606,7 @@ void run_group(const Par &P, int64_t r0, int64_t r1, const int64_t *read_base_of
         out.st.int_ops += R.int_ops;
         out.st.full_cells += R.full_cells;
         (R.bits == 16 ? out.st.n_align_i16 : out.st.n_align_i32)++;
-        if (R.max_width > out.st.reserved[0]) out.st.reserved[0] = R.max_width;  // widest band row (scheduling calibration)
+        if (R.max_width > out.st.max_band_width) out.st.max_band_width = R.max_width;  // widest band row (scheduling calibration)
         if (tr && tr->read_score) tr->read_score[r] = R.best_score;
         if (tr && tr->read_bits) tr->read_bits[r] = R.bits;
         if (tr && tr->read_band_cells) tr->read_band_cells[r] = R.band_cells;
@@ -622,7 +622,8 @@ void add_stats(mpoa_stats &a, const mpoa_stats &b) {
     a.n_groups += b.n_groups; a.n_reads += b.n_reads; a.n_alignments += b.n_alignments;
     a.band_cells += b.band_cells; a.full_cells += b.full_cells; a.int_ops += b.int_ops;
     a.n_align_i16 += b.n_align_i16; a.n_align_i32 += b.n_align_i32;
-    if (b.reserved[0] > a.reserved[0]) a.reserved[0] = b.reserved[0];
+    if (b.max_band_width > a.max_band_width) a.max_band_width = b.max_band_width;
+    a.n_seed_groups += b.n_seed_groups; a.n_seed_applied += b.n_seed_applied;
 }
 
 }  // namespace

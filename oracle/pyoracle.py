@@ -33,7 +33,8 @@ class _Stats(C.Structure):
                 ("n_align_i16", C.c_int64), ("n_align_i32", C.c_int64), ("tb_bytes", C.c_int64),
                 ("n_retry_groups", C.c_int64), ("kernel_ms", C.c_double), ("h2d_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("n_kernel_launches", C.c_int64), ("phase_cycles", C.c_int64 * 6),
-                ("reserved", C.c_int64 * 2)]
+                ("n_seed_groups", C.c_int64), ("n_seed_applied", C.c_int64), ("n_too_big_groups", C.c_int64),
+                ("max_band_width", C.c_int64), ("reserved", C.c_int64 * 4)]
 
 
 class _Trace(C.Structure):
@@ -131,5 +132,4 @@ def oracle_consensus_batch(groups=None, packed=None, params=None, n_threads=1, t
     raw = cons_buf.tobytes()
     cons = [raw[cons_off[i]:cons_off[i + 1]] for i in range(ng)]
     stats = {k: getattr(st, k) for k, _ in _Stats._fields_ if k not in ("reserved", "phase_cycles")}
-    stats["max_band_width"] = int(st.reserved[0])
     return dict(cons=cons, status=status, stats=stats, trace=tr_arrays)

@@ -2,7 +2,8 @@
 it at utils/SpliceDefineConsensus.py:10 and defineIsoforms.py:12).  It gives the UNMODIFIED
 reference code something to import so that its own control flow can be run here:
 
-  Aligner(seq=, preset=).map(seq) -> hits with .is_primary / .strand   (k-mer strand vote)
+  Aligner(seq=, preset=).map(seq) -> hits with .is_primary / .strand   (the library's own seed-chain
+                                     stage of map-ont, mpoa_orient_batch: host code, no GPU)
   revcomp(seq), fastx_read(path)
 
 It also seeds NumPy's global RNG from $MANDO_TEST_SEED at import: the reference never seeds it
@@ -14,7 +15,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-from mandalorion_b200.consensus import KmerOrienter, revcomp as _revcomp  # noqa: E402
+from mandalorion_b200.consensus import NativeOrienter, revcomp as _revcomp  # noqa: E402
 
 if os.environ.get("MANDO_TEST_SEED"):
     np.random.seed(int(os.environ["MANDO_TEST_SEED"]))
@@ -28,7 +29,7 @@ class _Hit:
 
 class Aligner:
     def __init__(self, seq=None, preset=None, **kw):
-        self._o = KmerOrienter(seq)
+        self._o = NativeOrienter(seq)
 
     def map(self, seq):
         for s in self._o.hits(seq):

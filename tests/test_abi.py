@@ -25,7 +25,7 @@ def test_header_symbols_are_exported(built):
         assert hasattr(lib, s), f"{s} declared in the header but not exported"
     assert sorted(ABI_SYMBOLS) == syms
     lib.mpoa_abi_version.restype = ctypes.c_int
-    assert lib.mpoa_abi_version() == 1
+    assert lib.mpoa_abi_version() == 2
 
 
 def test_default_params_are_the_reference_command_line(built):
@@ -42,7 +42,7 @@ def test_default_params_are_the_reference_command_line(built):
 def test_struct_layouts_match_the_header(built):
     from mandalorion_b200.poa import _Params, _Stats, _Trace
     assert ctypes.sizeof(_Params) == 4 * 16
-    assert ctypes.sizeof(_Stats) == 8 * 22
+    assert ctypes.sizeof(_Stats) == 8 * 28
     assert ctypes.sizeof(_Trace) == 8 * 5
 
 

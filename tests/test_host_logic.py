@@ -38,13 +38,18 @@ def test_orientation_and_dropping():
     reads = [("a", t), ("b", revcomp(t.encode()).decode()), ("c", other), ("d", t[5:-7])]
     # a permutation whose first read belongs to the isoform (the reference aligns everything to read 0)
     seed = next(s for s in range(50) if np.random.RandomState(s).choice(np.arange(0, 4), 4, replace=False)[0] != 2)
-    pg = C.prepare_group(reads, rng=np.random.RandomState(seed), orienter_factory=C.KmerOrienter)
+    pg = C.prepare_group(reads, rng=np.random.RandomState(seed), orienter_factory=C.NativeOrienter)
     first = pg.sequences[0]
     # every kept read is in the orientation of the first one; the unrelated read is dropped,
     # but its length still counts for the -S decision (seq_lengths records every read, :901)
     assert len(pg.sequences) == 3 and len(pg.seq_lengths) == 4
-    k = C.KmerOrienter(first)
+    k = C.NativeOrienter(first)
     assert all(k.hits(s) == [1] for s in pg.sequences)
+    # the batched path (orientation pending until the groups are flushed) gives the same group
+    pg2 = C.prepare_group(reads, rng=np.random.RandomState(seed))
+    if pg2.sequences is None:                          # mappy absent: deferred to one native call
+        C.orient_pending([pg2])
+    assert pg2.sequences == pg.sequences and pg2.bypass == pg.bypass and pg2.seq_lengths == pg.seq_lengths
     assert other not in pg.sequences and revcomp(other.encode()).decode() not in pg.sequences
 
 
@@ -63,7 +68,7 @@ def test_determine_consensus_matches_the_reference_flow():
         np.random.seed(7)
         idx = reference_subsample(len(reads))
         np.random.seed(7)
-        cons, names = C.determine_consensus(reads, "unused_root", "unused_abpoa", ctx=ctx, orienter_factory=C.KmerOrienter)
+        cons, names = C.determine_consensus(reads, "unused_root", "unused_abpoa", ctx=ctx, orienter_factory=C.NativeOrienter)
         assert names == [r[0] for r in reads]
         seqs = [reads[i][1] for i in idx]
         if len(seqs) <= 2:
@@ -110,13 +115,13 @@ def test_locus_dispatch_and_writer(tmp_path):
             ("chr2~50~700", {"1": groups[4], "2": groups[5], "3": groups[6]})]
     ctx = OracleBackedContext()
     np.random.seed(99)
-    res = C.consensus_for_loci(loci, ctx=ctx, orienter_factory=C.KmerOrienter)
+    res = C.consensus_for_loci(loci, ctx=ctx, orienter_factory=C.NativeOrienter)
     assert ctx.calls <= 1                                # ONE batched call for all loci
     # the serial reference flow with the same seed gives the same IsoData
     np.random.seed(99)
     for root, seq_dict in loci:
         for isoform, reads in seq_dict.items():
-            cons, names = C.determine_consensus(reads, ctx=OracleBackedContext(), orienter_factory=C.KmerOrienter)
+            cons, names = C.determine_consensus(reads, ctx=OracleBackedContext(), orienter_factory=C.NativeOrienter)
             assert res[root][isoform] == [cons, names]
     n = C.write_isoform_files([r for r, _ in loci], res, str(tmp_path))
     assert n == 7
