@@ -20,12 +20,15 @@ class OracleBackedContext:
     def run(self):
         self.calls += 1
         self._out = oracle_consensus_batch(packed=self._packed, params=self.params)
-        return self._out["stats"]
+        st = dict(self._out["stats"])
+        st.setdefault("kernel_ms", 1.0)
+        st["kernel_ms"] = st["kernel_ms"] or 1.0
+        return st
 
     def fetch(self, trace=False):
         return dict(cons=self._out["cons"], status=self._out["status"], trace=None)
 
-    def consensus_batch(self, groups=None, packed=None, trace=False):
+    def consensus_batch(self, groups=None, packed=None, trace=False, flags=None):
         self.upload(*(packed if packed is not None else pack_groups(groups)))
         st = self.run()
         out = self.fetch()

@@ -1,0 +1,58 @@
+"""Large GPU-vs-oracle sweeps (-m gpu): thousands of groups of the named configs and a
+hypothesis-driven fuzz over read length / depth / error rate / scoring parameters.  The oracle
+(all host threads) is the checker; bit-exact consensus, scores, band-cell counts and
+per-base node identities."""
+import os
+
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+from helpers import OracleParams, oracle_consensus_batch, pack_groups
+from mandalorion_b200 import PoaContext, PoaParams
+from mandalorion_b200.synth import GroupConfig, make_groups
+from test_gpu_parity import assert_same
+
+pytestmark = pytest.mark.gpu
+THREADS = os.cpu_count() or 1
+
+
+@pytest.mark.parametrize("cfg,n,first", [("cfg1", 1000, 0), ("cfg2", 2048, 20000), ("cfg4", 48, 100), ("cfg3", 48, 100)])
+def test_parity_sweep_of_the_named_configs(gpu_ctx, cfg, n, first):
+    groups = make_groups(cfg, n, first=first)
+    packed = pack_groups(groups)
+    want = oracle_consensus_batch(packed=packed, trace=True, n_threads=THREADS)
+    got = gpu_ctx.consensus_batch(packed=packed, trace=True)
+    assert_same(got, want, packed)
+    assert (got["status"] == 0).all()
+
+
+def test_junk_long_reads_leave_the_packed_path_and_still_match(gpu_ctx):
+    """unrelated 7-9 kb reads: alignment scores fall far below the diagonal, the packed kernel hands the
+    group to the int32 kernel (ST_RETRY_32) -- on the GPU, never on the CPU -- and the result is the oracle's"""
+    rng = np.random.default_rng(4)
+    groups = [["".join(rng.choice(list("ACGT"), int(rng.integers(7000, 9000)))) for _ in range(3)] for _ in range(3)]
+    groups += make_groups("cfg3", 2)
+    packed = pack_groups(groups)
+    want = oracle_consensus_batch(packed=packed, trace=True, n_threads=THREADS)
+    got = gpu_ctx.consensus_batch(packed=packed, trace=True)
+    assert_same(got, want, packed)
+    assert got["stats"]["n_retry_groups"] >= 3 and got["stats"]["n_kernel_launches"] >= 2
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(seed=st.integers(0, 2 ** 31 - 1), len_lo=st.integers(20, 3000), spread=st.integers(0, 600),
+       reads_hi=st.integers(3, 24), err=st.sampled_from([0.0, 0.002, 0.01, 0.03, 0.08, 0.2]),
+       mix=st.sampled_from([(0.3, 0.35, 0.35), (1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0), (0.2, 0.4, 0.4)]),
+       pk=st.sampled_from([{}, {}, {}, dict(simd_pn_i16=8, simd_pn_i32=4), dict(simd_pn_i16=32, simd_pn_i32=16),
+                           dict(match=2), dict(wb=4, wf=0.0), dict(wb=60), dict(wb=130, simd_pn_i16=8),
+                           dict(gap_open1=6, gap_ext1=3, gap_open2=30, gap_ext2=2, mismatch=6), dict(match=1, mismatch=9)]))
+def test_fuzz_lengths_depths_errors_parameters(built, seed, len_lo, spread, reads_hi, err, mix, pk):
+    cfg = GroupConfig("fz%d" % (seed % 1000), 6, 1, reads_hi, len_lo, len_lo + spread, "uniform", err, mix)
+    rng = np.random.default_rng(seed)
+    groups = make_groups(cfg, first=int(rng.integers(0, 10 ** 6)))
+    packed = pack_groups(groups)
+    want = oracle_consensus_batch(packed=packed, trace=True, params=OracleParams(**pk), n_threads=THREADS)
+    with PoaContext(0, PoaParams(**pk)) as ctx:
+        got = ctx.consensus_batch(packed=packed, trace=True)
+    assert_same(got, want, packed)
