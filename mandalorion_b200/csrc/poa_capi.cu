@@ -84,8 +84,8 @@ struct mpoa_ctx {
     DevBuf b_ascii, b_codes, b_rbo, b_gro, b_region, b_len, b_status, b_queue, b_out_off, b_out;
     DevBuf b_tr_score, b_tr_bits, b_tr_cells, b_tr_aln, b_tr_node;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaStream_t side = nullptr;
-    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+    cudaStream_t side = nullptr, side2 = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr, join2_ev = nullptr;
     double h2d_ms = 0;
     bool ran = false;
     std::vector<int32_t> h_status;
@@ -166,7 +166,9 @@ extern "C" void mpoa_destroy(mpoa_ctx *ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
+    if (ctx->join2_ev) cudaEventDestroy(ctx->join2_ev);
     if (ctx->side) cudaStreamDestroy(ctx->side);
+    if (ctx->side2) cudaStreamDestroy(ctx->side2);
     delete ctx;
 }
 
@@ -355,6 +357,8 @@ struct Launch {
     uint64_t ws_off = 0;
     size_t q_off = 0;
     bool small = false;          // too few groups to fill the GPU: runs beside the big launches
+    bool own_ws = false;         // big launch with a workspace of its own (may overlap the previous one's tail)
+    uint64_t big_off = 0;
 };
 
 static void fill_args(mpoa_ctx *ctx, const Launch &ln, int k, KernelArgs &A) {
@@ -367,6 +371,7 @@ static void fill_args(mpoa_ctx *ctx, const Launch &ln, int k, KernelArgs &A) {
     A.tr_score = ctx->d_tr_score; A.tr_bits = ctx->d_tr_bits; A.tr_cells = ctx->d_tr_cells;
     A.tr_aln = ctx->d_tr_aln; A.tr_node = ctx->d_tr_node;
     A.level = ln.lv;
+    A.tbcap_words = (uint32_t)std::min<uint64_t>(ln.L.tbcap / 4, 0xfffff000ull);
     const mpoa_params &p = ctx->params;
     A.P.match = std::abs(p.match); A.P.mismatch = std::abs(p.mismatch);
     A.P.o1 = p.gap_open1; A.P.e1 = p.gap_ext1; A.P.o2 = p.gap_open2; A.P.e2 = p.gap_ext2;
@@ -429,6 +434,16 @@ static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_la
         const uint64_t bytes = (uint64_t)nb * tpb * ln->L.slot_bytes;
         if (ln->small) { ln->ws_off = need_small; need_small += bytes; } else need_big = std::max(need_big, bytes);
     }
+    /* big launches overlap their tails when every one of them can have its own workspace */
+    {
+        uint64_t sum_big = 0;
+        for (Launch *ln : live) if (!ln->small) sum_big += (uint64_t)ln->n_blocks * ln->wpb * (32 / ln->c.T) * ln->L.slot_bytes;
+        if (n_big > 1 && sum_big + need_small <= budget) {
+            uint64_t off = 0;
+            for (Launch *ln : live) if (!ln->small) { ln->own_ws = true; ln->big_off = off; off += (uint64_t)ln->n_blocks * ln->wpb * (32 / ln->c.T) * ln->L.slot_bytes; }
+            need_big = sum_big;
+        }
+    }
     if (need_small > budget / 2) {                    // too much for side by side: everything back to back
         for (Launch *ln : live) { if (ln->small) need_big = std::max(need_big, (uint64_t)ln->n_blocks * ln->wpb * (32 / ln->c.T) * ln->L.slot_bytes); ln->small = false; }
         need_small = 0;
@@ -444,7 +459,7 @@ static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_la
     std::vector<int32_t> hq;
     bool any_small = false;
     for (Launch *ln : live) {
-        ln->ws_off = ln->small ? need_big + ln->ws_off : 0;
+        ln->ws_off = ln->small ? need_big + ln->ws_off : (ln->own_ws ? ln->big_off : 0);
         ln->q_off = q_off;
         q_off += ln->gs.size();
         hq.insert(hq.end(), ln->gs.begin(), ln->gs.end());
@@ -453,7 +468,8 @@ static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_la
     if (live.size() > 16) { ctx->err = "too many launch levels"; return MPOA_EINVAL; }
     CK(cudaMemcpyAsync(ctx->d_queue, hq.data(), hq.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_queue_head, 0, 16 * sizeof(int), ctx->stream));
-    if (any_small) {
+    bool used_side2 = false;
+    if (any_small || n_big > 1) {
         if (!ctx->side) CK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
         if (!ctx->fork_ev) CK(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
         if (!ctx->join_ev) CK(cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming));
@@ -461,6 +477,8 @@ static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_la
         CK(cudaStreamWaitEvent(ctx->side, ctx->fork_ev, 0));
     }
     const bool verbose = getenv("MPOA_VERBOSE") != nullptr;
+    const bool overlap = getenv("MPOA_NO_OVERLAP") == nullptr;
+    bool first_big = true;
     for (size_t k = 0; k < live.size(); ++k) {
         Launch *ln = live[k];
         if (ln->n_blocks <= 0) {
@@ -471,6 +489,17 @@ static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_la
         KernelArgs A;
         fill_args(ctx, *ln, (int)k, A);
         cudaStream_t st = ln->small ? ctx->side : ctx->stream;
+        if (!ln->small && !first_big && overlap && ln->own_ws) {
+            /* the next big launch waits on ANOTHER stream for SM slots: its blocks move in while the
+             * previous launch drains its last groups (the persistent blocks of a launch retire one by
+             * one), instead of after the last one has gone */
+            if (!ctx->side2) CK(cudaStreamCreateWithFlags(&ctx->side2, cudaStreamNonBlocking));
+            if (!ctx->join2_ev) CK(cudaEventCreateWithFlags(&ctx->join2_ev, cudaEventDisableTiming));
+            CK(cudaStreamWaitEvent(ctx->side2, ctx->fork_ev, 0));
+            st = ctx->side2;
+            used_side2 = true;
+        }
+        if (!ln->small) first_big = false;
         CK(launch_poa(ln->c.code(), A, (int)ln->n_blocks, ln->wpb, st));
         ++*n_launch;
         if (verbose)
@@ -478,9 +507,13 @@ static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_la
                     ln->c.T, ln->c.WPL, ln->c.wcap, ln->gs.size(), (long long)ln->n_blocks, ln->wpb, ln->bps,
                     ln->L.slot_bytes / 1e6, ln->small ? " (side stream)" : "");
     }
-    if (any_small) {
+    if (any_small || n_big > 1) {
         CK(cudaEventRecord(ctx->join_ev, ctx->side));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0));
+    }
+    if (used_side2) {
+        CK(cudaEventRecord(ctx->join2_ev, ctx->side2));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->join2_ev, 0));
     }
     return MPOA_OK;
 }

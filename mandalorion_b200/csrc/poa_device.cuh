@@ -85,6 +85,7 @@ struct KernelArgs {
     int32_t *tr_aln, *tr_node;
     DevParams P;
     Packed16 K;
+    uint32_t tbcap_words;            // traceback area of a slot in 32-bit words (capped to 32-bit offsets)
     int wcap;                        // cells per ring row
     int level;                       // host launch level, reported back with the retry codes
 };

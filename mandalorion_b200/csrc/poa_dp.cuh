@@ -390,7 +390,7 @@ __device__ __forceinline__ int dp_band16(const KernelArgs &A, const Slot &S, con
     const int N = tm.uniform(N_in), qlen = tm.uniform(qlen_in);
     const uint32_t *in_off = in_off_p(A, S), *in_row = in_row_p(A, S);
     uint32_t *tb = reinterpret_cast<uint32_t *>(tb_p(A, S));   // words = pairs of int16 cells
-    const uint32_t tbcap = pin_reg((uint32_t)min(A.L.tbcap / 4, (uint64_t)0xfffff000u));
+    const uint32_t tbcap = A.tbcap_words;   // (a kernel parameter: used straight from the constant bank)
     lane_width_rule(P, qlen, N, R);
     /* sticky status of this team: a team that fails (or is switched off) keeps walking through the
      * loops with its stores disabled -- the other team of the warp needs the lockstep */
@@ -594,12 +594,11 @@ __device__ __forceinline__ int dp_band16(const KernelArgs &A, const Slot &S, con
             lds_words<WPL>(prof_a + nbase * (RW * 4), S2);
             const uint32_t stw = cur_stw;
             const uint32_t tbo = tb_used;
-            bool st_ok = rowon && err == ST_OK;   // (a re-bind may just have failed)
-            if (st_ok) {
-                tb_used = tbo + 3 * stw;
-                cells += B.width;
-                if (tb_used > tbcap) { st_ok = false; err = ST_RETRY; }
-            }
+            const bool want = rowon && err == ST_OK;   // (a re-bind may just have failed)
+            const bool st_ok = want && tbo + 3 * stw <= tbcap;
+            tb_used = st_ok ? tbo + 3 * stw : tbo;
+            cells += st_ok ? (uint32_t)B.width : 0u;
+            if (want && !st_ok) err = ST_RETRY;
 
             /* diagonal and deletion inputs */
             uint32_t M2[WPL], EA[WPL], EB[WPL];
