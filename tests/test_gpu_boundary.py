@@ -178,3 +178,22 @@ def test_dstep_with_native_orientation_on_the_gpu(gpu_ctx, tmp_path, monkeypatch
         seqs = [s if h == [1] else revcomp(s.encode()).decode() for s, h in zip(sub, fwd)]
         want = seqs[0] if len(seqs) <= 2 else (oracle_consensus_batch([seqs])["cons"][0].decode() or seqs[0])
         assert results["chr1~%d~%d" % (g * 1000, g * 1000 + 900)]["1"][0] == want
+
+
+def test_streaming_dispatch_on_the_gpu(gpu_ctx, monkeypatch):
+    """loci fed one by one, GPU batches issued in the background: same IsoData as the collect-everything path"""
+    from mandalorion_b200 import dstep
+    monkeypatch.setattr(cons_mod, "mappy_available", lambda: False)
+    groups = make_groups("cfg1", 48, random_strand=True, with_names=True)
+
+    def prepared():
+        np.random.seed(11)
+        return {"chr2~%d~%d" % (g * 1000, g * 1000 + 900): {"1": cons_mod.prepare_group(reads)} for g, reads in enumerate(groups)}
+
+    want = cons_mod.finish_prepared(prepared(), ctx=gpu_ctx)
+    sc = dstep.StreamingConsensus(gpu_ctx, batch_bases=150000)
+    for root, iso in prepared().items():
+        sc.add_locus(root, iso)
+    got = sc.finish()
+    assert got == want and sc.n_batches >= 3
+    assert sum(st["n_groups"] for st in sc.stats) == sum(1 for r in want if len(groups[int(r.split("~")[1]) // 1000]) > 2)
