@@ -49,7 +49,22 @@ extern "C" {
 
 /* group_flags bits */
 #define MPOA_FLAG_SEED   1u    /* the reference would have passed -S (median read length
-                                  >= 8000, utils/SpliceDefineConsensus.py:916-919) */
+                                  >= 8000, utils/SpliceDefineConsensus.py:916-919): the group is
+                                  aligned window by window between minimizer anchors, see
+                                  "Seeded groups" below */
+
+/*
+ * Seeded groups (abpoa -S).  abPOA's seeding code (upstream abpoa_seed.c) is not part of the
+ * reference tree; what this library implements is the structure SURVEY.md A.10 records -- (k, w)
+ * minimizers of consecutive reads, colinear chaining of their hits, anchors at least MIN_W apart,
+ * every anchor k-mer a forced run of matches, the stretches between anchors aligned to the
+ * sub-graph between the anchor nodes -- with the rules of csrc/seed.cpp for everything the summary
+ * leaves open.  The CPU oracle restates the same rules independently; neither is pinned against a
+ * real `abpoa -S` run (none is reachable from the build image).
+ */
+#define MPOA_SEED_K      19
+#define MPOA_SEED_W      10
+#define MPOA_SEED_MIN_W  500
 
 /*
  * Scoring / band parameters == the abpoa command line of the reference.

@@ -56,10 +56,7 @@ def main(argv=None):
     reads = read_fasta(path)
     if not reads:
         return 0
-    if seed:
-        # abpoa -S = minimizer-seeded, windowed alignment (reference :919, median read length >= 8000);
-        # this library aligns every group unseeded and says so (stderr goes to abpoa.messages in the reference)
-        sys.stderr.write("abpoa-b200: -S accepted, but the group is aligned WITHOUT minimizer seeding\n")
+    # -S = minimizer-seeded, windowed alignment (reference :919, median read length >= 8000): MPOA_FLAG_SEED
     with PoaContext(0, params) as ctx:
         out = ctx.consensus_batch([reads], flags=[1 if seed else 0])
     if out["status"][0] == 0 and out["cons"][0]:

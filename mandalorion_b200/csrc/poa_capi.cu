@@ -14,6 +14,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mandalorion_poa.h"
@@ -22,7 +23,9 @@
 namespace mpoa {
 cudaError_t launch_encode(const uint8_t *ascii, uint8_t *codes, int64_t n, cudaStream_t stream);
 cudaError_t launch_poa(int code, const KernelArgs &A, int n_blocks, int warps_per_block, cudaStream_t stream);
-int poa_max_blocks_per_sm(int code, int wcap, int warps_per_block);
+int poa_max_blocks_per_sm(int code, int wcap, int warps_per_block, bool seeded);
+void seed_batch(int64_t n_groups, const int64_t *gro, const int64_t *rbo, const uint8_t *bases, const uint8_t *flags,
+                int k, int w, int min_gap, int n_threads, std::vector<int32_t> &anc_off, std::vector<int32_t> &anc);
 size_t poa_smem_bytes(int code, int wcap, int warps_per_block);
 bool variant_exists(int code);
 cudaError_t launch_int_peak(uint32_t *out, int blocks, int iters, cudaStream_t stream);
@@ -82,7 +85,10 @@ struct mpoa_ctx {
     uint8_t *d_ws = nullptr;
     size_t ws_bytes = 0;
     DevBuf b_ascii, b_codes, b_rbo, b_gro, b_region, b_len, b_status, b_queue, b_out_off, b_out;
-    DevBuf b_tr_score, b_tr_bits, b_tr_cells, b_tr_aln, b_tr_node;
+    DevBuf b_tr_score, b_tr_bits, b_tr_cells, b_tr_aln, b_tr_node, b_anc_off, b_anc;
+    int32_t *d_anc_off = nullptr;
+    int2 *d_anc = nullptr;
+    int64_t n_seed_groups = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t side = nullptr, side2 = nullptr;
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr, join2_ev = nullptr;
@@ -106,13 +112,14 @@ static void free_batch(mpoa_ctx *ctx) {   // forgets the uploaded batch; device 
     ctx->d_cons_len = ctx->d_status = ctx->d_queue = nullptr;
     ctx->d_tr_score = ctx->d_tr_bits = ctx->d_tr_aln = ctx->d_tr_node = nullptr; ctx->d_tr_cells = nullptr;
     ctx->n_groups = ctx->n_reads = ctx->n_bases = 0;
+    ctx->d_anc_off = nullptr; ctx->d_anc = nullptr; ctx->n_seed_groups = 0;
     ctx->ran = false;
 }
 
 static void release_buffers(mpoa_ctx *ctx) {
     for (DevBuf *b : {&ctx->b_ascii, &ctx->b_codes, &ctx->b_rbo, &ctx->b_gro, &ctx->b_region, &ctx->b_len, &ctx->b_status,
                       &ctx->b_queue, &ctx->b_out_off, &ctx->b_out, &ctx->b_tr_score, &ctx->b_tr_bits, &ctx->b_tr_cells,
-                      &ctx->b_tr_aln, &ctx->b_tr_node})
+                      &ctx->b_tr_aln, &ctx->b_tr_node, &ctx->b_anc_off, &ctx->b_anc})
         b->release();
 }
 
@@ -286,6 +293,22 @@ extern "C" int mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups, const int64_t 
     std::vector<int64_t> region(n_groups + 1);
     for (int64_t g = 0; g <= n_groups; ++g) region[g] = ctx->h_rbo[ctx->h_gro[g]];
     CK(cudaMemcpyAsync(ctx->d_region_off, region.data(), (n_groups + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    /* `abpoa -S` groups: their anchors are computed here, on the host threads, while the copies are in flight */
+    ctx->n_seed_groups = 0;
+    for (uint8_t f : ctx->h_flags) ctx->n_seed_groups += (f & MPOA_FLAG_SEED) ? 1 : 0;
+    if (ctx->n_seed_groups > 0) {
+        std::vector<int32_t> anc_off, anc;
+        const int nt = (int)std::max(1u, std::thread::hardware_concurrency());
+        seed_batch(n_groups, ctx->h_gro.data(), ctx->h_rbo.data(), bases, ctx->h_flags.data(), MPOA_SEED_K, MPOA_SEED_W,
+                   MPOA_SEED_MIN_W, nt, anc_off, anc);
+        if (getenv("MPOA_SEED_NOANCHOR")) { std::fill(anc_off.begin(), anc_off.end(), 0); anc.clear(); }   // debugging aid
+        CK(ctx->b_anc_off.ensure(anc_off.size() * sizeof(int32_t)));
+        CK(ctx->b_anc.ensure(std::max<size_t>(anc.size(), 2) * sizeof(int32_t)));
+        ctx->d_anc_off = (int32_t *)ctx->b_anc_off.p; ctx->d_anc = (int2 *)ctx->b_anc.p;
+        CK(cudaMemcpyAsync(ctx->d_anc_off, anc_off.data(), anc_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        if (!anc.empty()) CK(cudaMemcpyAsync(ctx->d_anc, anc.data(), anc.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));   // anc_off / anc are locals
+    }
     CK(launch_encode(d_ascii, ctx->d_codes, n_bases, ctx->stream));
     if (ctx->want_trace) {
         const size_t nr = (size_t)std::max<int64_t>(n_reads, 1);
@@ -314,7 +337,7 @@ struct Caps {
 
 static uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
-static SlotLayout make_layout(const Caps &c) {
+static SlotLayout make_layout(const Caps &c, bool seeded) {
     SlotLayout L;
     std::memset(&L, 0, sizeof(L));
     L.ncap = c.ncap; L.ecap = c.ecap; L.qcap = c.qcap; L.tbcap = c.tbcap;
@@ -326,8 +349,12 @@ static SlotLayout make_layout(const Caps &c) {
         L.in_off[p] = take(n * 4); L.in_row[p] = take(e * 4);
         L.out_off[p] = take(n * 4); L.out_row[p] = take(e * 4); L.out_w[p] = take(e * 4);
     }
-    L.remain = take(n * 4); L.meta = take(n * 4); L.rowinfo = take(n * 16); L.rowtb = take(n * 16);
-    L.rowbest = take(n * 4); L.qmap = take(q * 4);
+    L.remain[0] = take(n * 4); L.meta[0] = take(n * 4); L.rowinfo = take(n * 16); L.rowtb = take(n * 16);
+    L.rowbest = take(n * 4); L.qmap[0] = take(q * 4);
+    if (seeded) {       // the sub-graph view of a window (poa_seed.cuh) and the previous read's rows
+        L.in_off[2] = take(n * 4); L.in_row[2] = take(e * 4); L.remain[1] = take(n * 4); L.meta[1] = take(n * 4);
+        L.qmap[1] = take(q * 4); L.prevrow = take(q * 4);
+    }
     L.qprof = take(4ull * qprof_stride(c.qcap) * 4);
     L.pv = take(q * 4); L.pkey = take(q * 4); L.pnew = take(q * 4); L.psib = take(q * 4);
     L.nin = take(q * 4); L.nout = take(q * 4);
@@ -356,6 +383,7 @@ struct Launch {
     int64_t n_blocks = 0;
     uint64_t ws_off = 0;
     size_t q_off = 0;
+    bool seeded = false;         // `abpoa -S` groups: the windowed kernel instantiation
     bool small = false;          // too few groups to fill the GPU: runs beside the big launches
     bool own_ws = false;         // big launch with a workspace of its own (may overlap the previous one's tail)
     uint64_t big_off = 0;
@@ -371,6 +399,7 @@ static void fill_args(mpoa_ctx *ctx, const Launch &ln, int k, KernelArgs &A) {
     A.tr_score = ctx->d_tr_score; A.tr_bits = ctx->d_tr_bits; A.tr_cells = ctx->d_tr_cells;
     A.tr_aln = ctx->d_tr_aln; A.tr_node = ctx->d_tr_node;
     A.level = ln.lv;
+    if (ln.seeded) { A.anc_off = ctx->d_anc_off; A.anc = ctx->d_anc; A.seed_k = MPOA_SEED_K; }
     A.tbcap_words = (uint32_t)std::min<uint64_t>(ln.L.tbcap / 4, 0xfffff000ull);
     const mpoa_params &p = ctx->params;
     A.P.match = std::abs(p.match); A.P.mismatch = std::abs(p.mismatch);
@@ -404,14 +433,14 @@ static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_la
         ln.wpb = 4;
         while (ln.wpb > 1 && poa_smem_bytes(ln.c.code(), ln.c.wcap, ln.wpb) > ctx->smem_optin) ln.wpb >>= 1;
         ln.bps = poa_smem_bytes(ln.c.code(), ln.c.wcap, ln.wpb) > ctx->smem_optin
-                     ? 0 : poa_max_blocks_per_sm(ln.c.code(), ln.c.wcap, ln.wpb);
+                     ? 0 : poa_max_blocks_per_sm(ln.c.code(), ln.c.wcap, ln.wpb, ln.seeded);
         if (ln.bps <= 0) {
             ctx->err = "band wider than shared memory allows";
             for (int32_t g : ln.gs) ctx->h_status[g] = ST_TOO_BIG;
             continue;
         }
         if (const char *b = getenv("MPOA_BPS")) ln.bps = std::min(ln.bps, std::max(1, atoi(b)));   // tuning aid
-        ln.L = make_layout(ln.c);
+        ln.L = make_layout(ln.c, ln.seeded);
         live.push_back(&ln);
     }
     if (live.empty()) return MPOA_OK;
@@ -503,9 +532,9 @@ static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_la
         CK(launch_poa(ln->c.code(), A, (int)ln->n_blocks, ln->wpb, st));
         ++*n_launch;
         if (verbose)
-            fprintf(stderr, "[mpoa] level T=%d WPL=%d wcap=%d groups=%zu blocks=%lld x %d warps (bps %d) slot=%.1f MB%s\n",
+            fprintf(stderr, "[mpoa] level T=%d WPL=%d wcap=%d groups=%zu blocks=%lld x %d warps (bps %d) slot=%.1f MB%s%s\n",
                     ln->c.T, ln->c.WPL, ln->c.wcap, ln->gs.size(), (long long)ln->n_blocks, ln->wpb, ln->bps,
-                    ln->L.slot_bytes / 1e6, ln->small ? " (side stream)" : "");
+                    ln->L.slot_bytes / 1e6, ln->small ? " (side stream)" : "", ln->seeded ? " seeded" : "");
     }
     if (any_small || n_big > 1) {
         CK(cudaEventRecord(ctx->join_ev, ctx->side));
@@ -560,21 +589,28 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
          * the next wider level of the same lane family when that one fills the GPU (every group runs
          * correctly in any level at least as wide as its own); what stays small runs beside the big
          * launches (run_round) */
-        std::vector<std::vector<int32_t>> bins(kNumLevels);
-        for (int32_t g : pending) bins[ctx->ginfo[g].level].push_back(g);
+        /* bins [0, kNumLevels): unseeded groups per level; [kNumLevels, 2 kNumLevels): `abpoa -S` groups */
+        auto is_seeded = [&](int32_t g) { return !ctx->h_flags.empty() && (ctx->h_flags[g] & MPOA_FLAG_SEED) != 0; };
+        std::vector<std::vector<int32_t>> bins(2 * kNumLevels);
+        for (int32_t g : pending) bins[ctx->ginfo[g].level + (is_seeded(g) ? kNumLevels : 0)].push_back(g);
         const size_t min_groups = (size_t)ctx->n_sm * 16;
-        for (int a = 0; a < kNumLevels; ++a) {
-            if (bins[a].empty() || bins[a].size() >= min_groups) continue;
-            for (int o = a + 1; o < kNumLevels; ++o)
-                if (bins[o].size() >= min_groups && (kLevels[o].WPL == 0) == (kLevels[a].WPL == 0)) {
-                    bins[o].insert(bins[o].end(), bins[a].begin(), bins[a].end());
-                    bins[a].clear();
-                    break;
+        for (int half = 0; half < 2; ++half)
+            for (int a = 0; a < kNumLevels; ++a) {
+                auto &ba = bins[half * kNumLevels + a];
+                if (ba.empty() || ba.size() >= min_groups) continue;
+                for (int o = a + 1; o < kNumLevels; ++o) {
+                    auto &bo = bins[half * kNumLevels + o];
+                    if (bo.size() >= min_groups && (kLevels[o].WPL == 0) == (kLevels[a].WPL == 0)) {
+                        bo.insert(bo.end(), ba.begin(), ba.end());
+                        ba.clear();
+                        break;
+                    }
                 }
-        }
+            }
         std::vector<Launch> launches;
-        for (int lv = 0; lv < kNumLevels; ++lv) {
-            auto &gs = bins[lv];
+        for (int bi = 0; bi < 2 * kNumLevels; ++bi) {
+            const int lv = bi % kNumLevels;
+            auto &gs = bins[bi];
             if (gs.empty()) continue;
             /* heaviest first (longest-processing-time order keeps the tail of the launch short); for
              * two teams per warp: longest reads first, so that the groups the teams of one warp work on
@@ -613,6 +649,7 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
             c.tbcap = std::min<uint64_t>(tbmax + 4096, 0x3fff00000ull);
             launches.emplace_back();
             launches.back().lv = lv;
+            launches.back().seeded = bi >= kNumLevels;
             launches.back().gs = gs;
             launches.back().c = c;
         }
@@ -660,10 +697,9 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
     st.tb_bytes = (int64_t)hs[SI_TB];
     for (int k = 0; k < 6; ++k) st.phase_cycles[k] = (int64_t)hs[SI_T_PREP + k];
     st.n_kernel_launches = n_launch;
-    /* groups the reference would have run with `abpoa -S` (median read length >= 8000): this library
-     * aligns them WITHOUT minimizer seeding -- reported, never hidden (include/mandalorion_poa.h) */
-    for (uint8_t f : ctx->h_flags) st.n_seed_groups += (f & MPOA_FLAG_SEED) ? 1 : 0;
-    st.n_seed_applied = 0;
+    /* groups the reference would have run with `abpoa -S` (median read length >= 8000) */
+    st.n_seed_groups = ctx->n_seed_groups;
+    st.n_seed_applied = ctx->n_seed_groups;      // every kernel variant has its windowed instantiation
     for (int64_t g = 0; g < ng; ++g) st.n_too_big_groups += ctx->h_status[g] == ST_TOO_BIG ? 1 : 0;
     ctx->last = st;
     ctx->ran = true;

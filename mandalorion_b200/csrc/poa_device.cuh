@@ -57,8 +57,11 @@ struct Packed16 {
 struct SlotLayout {
     uint32_t ncap, ecap, qcap;
     uint64_t tbcap;                                    // bytes of the traceback area
-    uint64_t base[2], sib[2], creator[2], in_off[2], in_row[2], out_off[2], out_row[2], out_w[2];
-    uint64_t remain, meta, rowinfo, rowtb, rowbest, qmap;
+    /* [0], [1]: the double-buffered graph; in_off[2] / in_row[2], remain[1], meta[1], qmap[1]: the
+     * sub-graph view of a seeded window (zero-sized unless the launch is a seeded one) */
+    uint64_t base[2], sib[2], creator[2], in_off[3], in_row[3], out_off[2], out_row[2], out_w[2];
+    uint64_t remain[2], meta[2], rowinfo, rowtb, rowbest, qmap[2];
+    uint64_t prevrow;                                  // row of every base of the previous read (seeded launches)
     uint64_t qprof;                                    // query profile of the read being aligned: 4 bases x qprof_stride(qcap) words
     uint64_t pv, pkey, pnew, psib, nin, nout;          // per query position
     uint64_t cnt, addin, addout, grow, srcof;          // per row
@@ -83,6 +86,10 @@ struct KernelArgs {
     int32_t *tr_score, *tr_bits;     // optional trace (NULL when off)
     long long *tr_cells;
     int32_t *tr_aln, *tr_node;
+    /* `abpoa -S` launches: anchors (start in the previous read, start in this read) of every read */
+    const int32_t *anc_off;          // [n_reads+1]
+    const int2 *anc;
+    int seed_k;
     DevParams P;
     Packed16 K;
     uint32_t tbcap_words;            // traceback area of a slot in 32-bit words (capped to 32-bit offsets)
@@ -153,6 +160,8 @@ struct Team {
         if constexpr (T == 32) return p;
         else return __any_sync(FULL, p);
     }
+    /* any lane of the warp (the argument differs from lane to lane) */
+    __device__ __forceinline__ bool any_lane(bool p) const { return __any_sync(FULL, p); }
     __device__ __forceinline__ bool wall(bool p) const {
         if constexpr (T == 32) return p;
         else return __all_sync(FULL, p);

@@ -121,6 +121,7 @@ __device__ __forceinline__ int dp_align32(const KernelArgs &A, const Slot &S, in
             ring_info[0] = prev_info;
             rowinfo_p(A, S)[0] = prev_info;
             rowtb_p(A, S)[0] = make_uint4(0, stride, 0, 0);
+            if (meta_p(A, S)[0] & META_TOSINK) rowbest_p(A, S)[0] = hi == 0 ? 0 : max(-(P.o1 + P.e1 * hi), -(P.o2 + P.e2 * hi));   // (seeded windows only)
         }
         tb_used = 3 * stride;
         __syncwarp();
@@ -396,6 +397,7 @@ __device__ __forceinline__ int dp_band16(const KernelArgs &A, const Slot &S, con
      * loops with its stores disabled -- the other team of the warp needs the lockstep */
     int err = on ? ST_OK : ST_PENDING;
     if (R.pn & 3) err = ST_RETRY_32;          // band edges must fall on word pairs
+    if (N > 131071) err = ST_RETRY_32;        // remain is carried in 18 signed bits of the row metadata word
     const int hop1 = (P.e1 + P.match) * CPL, hop2 = (P.e2 + P.match) * CPL;   // what a lane hop costs the insertion scores
     if ((T - 1) * max(hop1, hop2) + P.match * CPL > 4700) err = ST_RETRY_32;   // head-room of the decay-free scan above/below NEG16
     const int lg = R.lgpn;
@@ -521,6 +523,9 @@ __device__ __forceinline__ int dp_band16(const KernelArgs &A, const Slot &S, con
             if (lane == 0) {
                 rowinfo_g[0] = make_int4(0, end_sn, 0, 0);
                 rowtb_g[0] = make_uint4(0, 2 * cur_stw, 0, 0);
+                /* the source can be a direct predecessor of the sink only in a seeded window with nothing
+                 * between its anchors: the read's stretch is then one insertion */
+                if (meta_p(A, S)[0] & META_TOSINK) rowbest_p(A, S)[0] = hi == 0 ? 0 : max(-(P.o1 + P.e1 * hi), -(P.o2 + P.e2 * hi));
             }
             tb_used = 3 * cur_stw;
         }
@@ -553,7 +558,7 @@ __device__ __forceinline__ int dp_band16(const KernelArgs &A, const Slot &S, con
             const bool rowon = l < nrows && err == ST_OK;   // this team computes a row in this step
             const uint32_t ma = tm.pick(m_a, l);   // uniform in the team
             const int nbase = ma & META_BASE;
-            const int rem = (int)(ma >> 14);
+            const int rem = (int)ma >> 14;     // signed: in a seeded window a row's heaviest path may by-pass the window's end
             const bool simple = (ma & 32u) != 0 || !rowon;
             const bool all_simple = tm.wall(simple);
             int npre = 1, in0 = 0, p0 = i - 1;

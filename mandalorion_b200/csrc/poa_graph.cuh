@@ -17,6 +17,7 @@ namespace mpoa {
 struct Slot {
     uint8_t *b;
     int par;
+    int sub;      // 1: the sub-graph view of a seeded window (in-edges, meta, remain, qmap)
 };
 
 #define MPOA_ACC(T, name)                                                                       \
@@ -30,11 +31,20 @@ struct Slot {
     __device__ __forceinline__ T *n_##name##_p(const KernelArgs &A, const Slot &S) {            \
         return reinterpret_cast<T *>(S.b + A.L.name[S.par ^ 1]);                                \
     }
+/* arrays that exist for the graph (S.sub = 0) and for the sub-graph view of a seeded window (S.sub = 1) */
+#define MPOA_ACCV(T, name, subidx)                                                              \
+    __device__ __forceinline__ T *name##_p(const KernelArgs &A, const Slot &S) {                \
+        return reinterpret_cast<T *>(S.b + (S.sub ? A.L.name[subidx] : A.L.name[0]));           \
+    }
 MPOA_ACC2(uint8_t, base) MPOA_ACC2(uint8_t, sib) MPOA_ACC2(int32_t, creator)
-MPOA_ACC2(uint32_t, in_off) MPOA_ACC2(uint32_t, in_row) MPOA_ACC2(uint32_t, out_off)
-MPOA_ACC2(uint32_t, out_row) MPOA_ACC2(int32_t, out_w)
-MPOA_ACC(int32_t, remain) MPOA_ACC(uint32_t, meta) MPOA_ACC(int4, rowinfo) MPOA_ACC(uint4, rowtb)
-MPOA_ACC(int32_t, rowbest) MPOA_ACC(int32_t, qmap) MPOA_ACC(uint32_t, qprof)
+MPOA_ACC2(uint32_t, out_off) MPOA_ACC2(uint32_t, out_row) MPOA_ACC2(int32_t, out_w)
+__device__ __forceinline__ uint32_t *in_off_p(const KernelArgs &A, const Slot &S) { return reinterpret_cast<uint32_t *>(S.b + A.L.in_off[S.sub ? 2 : S.par]); }
+__device__ __forceinline__ uint32_t *in_row_p(const KernelArgs &A, const Slot &S) { return reinterpret_cast<uint32_t *>(S.b + A.L.in_row[S.sub ? 2 : S.par]); }
+__device__ __forceinline__ uint32_t *n_in_off_p(const KernelArgs &A, const Slot &S) { return reinterpret_cast<uint32_t *>(S.b + A.L.in_off[S.par ^ 1]); }
+__device__ __forceinline__ uint32_t *n_in_row_p(const KernelArgs &A, const Slot &S) { return reinterpret_cast<uint32_t *>(S.b + A.L.in_row[S.par ^ 1]); }
+MPOA_ACCV(int32_t, remain, 1) MPOA_ACCV(uint32_t, meta, 1) MPOA_ACCV(int32_t, qmap, 1)
+MPOA_ACC(int4, rowinfo) MPOA_ACC(uint4, rowtb) MPOA_ACC(int32_t, prevrow)
+MPOA_ACC(int32_t, rowbest) MPOA_ACC(uint32_t, qprof)
 MPOA_ACC(int32_t, pv) MPOA_ACC(int32_t, pkey) MPOA_ACC(int32_t, pnew) MPOA_ACC(int32_t, psib)
 MPOA_ACC(int32_t, nin) MPOA_ACC(int32_t, nout)
 MPOA_ACC(int32_t, cnt) MPOA_ACC(int32_t, addin) MPOA_ACC(int32_t, addout) MPOA_ACC(int32_t, srcof)
@@ -46,6 +56,7 @@ __device__ __forceinline__ Slot make_slot(const KernelArgs &A, int slot, int par
     asm volatile("" : "+l"(S.b));   // keep the pointer in registers (it is otherwise re-derived at every access)
     __builtin_assume(__isGlobal(S.b));
     S.par = par;
+    S.sub = 0;
     return S;
 }
 
@@ -86,12 +97,13 @@ enum MetaBits { META_BASE = 7, META_TOSINK = 16 };
 /* ------------------------------------------------------------------------------------------ */
 
 /* first read = linear chain src -> b0 -> ... -> sink, every edge weight 1 */
-template <int T, bool TRACE>
+template <int T, bool TRACE, bool SEEDED>
 __device__ __forceinline__ void init_graph(const KernelArgs &A, const Slot &S, const Team<T> &tm, const uint8_t *seq, int len, int creator0) {
     const int N = len + 2;
     for (int r = tm.tl; r <= N; r += T) {
         if (r < N) {
             const bool real = r >= 1 && r <= len;
+            if constexpr (SEEDED) { if (real) prevrow_p(A, S)[r - 1] = r; }
             base_p(A, S)[r] = real ? seq[r - 1] : 0;
             sib_p(A, S)[r] = 0;
             if constexpr (TRACE) creator_p(A, S)[r] = real ? creator0 + r - 1 : -1;   // node identity: only the trace needs it
@@ -176,7 +188,7 @@ __device__ __forceinline__ void remain_pass(const KernelArgs &A, const Slot &S, 
  *     of their endpoints (edge order = first-creation order).
  * Returns ST_OK or ST_RETRY (capacity).
  */
-template <int T>
+template <int T, bool SEEDED = false>
 __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, const Team<T> &tm, int &par, int &N_io, int &E_io,
                                           const uint8_t *__restrict__ q, int qlen_in, int creator0, int32_t *tr_aln, int32_t *tr_node, bool on) {
     const int lane = tm.tl;
@@ -353,6 +365,7 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, co
             if (t <= qlen) {
                 const int from_new = from_old[u] >= 0 ? from_old[u] + cf[u] : km[u] + 1 + nm[u];
                 const int to_new = to_old[u] >= 0 ? to_old[u] + ct[u] : kt[u] + 1 + nt[u];
+                if constexpr (SEEDED) { if (t < qlen) prevrow_p(A, S)[t] = to_new; }   // where base t of this read lives in the merged graph
                 bool found = false;
                 if (o1[u] > o0[u]) {
                     if (e0[u] == to_old[u]) { out_w[o0[u]] = w0[u] + 1; found = true; }

@@ -15,6 +15,7 @@
  *   gather_consensus_kernel  per-group consensus regions -> one compact buffer
  */
 #include "poa_traceback.cuh"
+#include "poa_seed.cuh"
 
 namespace mpoa {
 
@@ -74,7 +75,7 @@ struct GroupState {
  * switch because the kernel's instruction footprint matters (resident warps share the
  * instruction cache).
  */
-template <int T, int WPL, bool TRACE>
+template <int T, int WPL, bool TRACE, bool SEEDED>
 __device__ __forceinline__ int read_step(const KernelArgs &A, const Team<T> &tm, int slot, GroupState &G, bool act, int *ring, int4 *ring_info,
                                          unsigned long long *st /* per-team counters in shared memory, lane 0 only */) {
     const int lane = tm.tl;
@@ -100,7 +101,7 @@ __device__ __forceinline__ int read_step(const KernelArgs &A, const Team<T> &tm,
             if (len <= 0) rc = ST_EMPTY;
             else if ((uint32_t)(len + 2) > A.L.ncap || (uint32_t)(len + 1) > A.L.ecap) rc = ST_RETRY;
             else {
-                init_graph<T, TRACE>(A, S, tm, seq, len, creator0);
+                init_graph<T, TRACE, SEEDED>(A, S, tm, seq, len, creator0);
                 G.N = len + 2; G.E = len + 1;
                 if constexpr (TRACE) {
                     for (int t = lane; t < len; t += T) { tr_aln[t] = -1; tr_node[t] = creator0 + t; }
@@ -119,28 +120,94 @@ __device__ __forceinline__ int read_step(const KernelArgs &A, const Team<T> &tm,
     long long tk1 = clock64();
     if (aln && lane == 0) st[SI_T_PREP] += tk1 - tk0;
     AlnState R;
-    int drc;
-    if constexpr (WPL == 0) drc = dp_align32(A, S, G.N, seq, len, ring, ring_info, lane, R);
-    else drc = dp_band16<T, WPL>(A, S, tm, G.N, seq, len, reinterpret_cast<uint32_t *>(ring), R, aln);
-    if (aln && drc != ST_OK) { rc = drc; aln = false; }
-    tk0 = clock64();
-    if (aln && lane == 0) {
-        st[SI_T_DP] += tk0 - tk1;
-        st[SI_CELLS] += R.cells; st[SI_INTOPS] += R.intops; st[SI_FULL] += R.full; st[SI_ALN] += 1;
-        st[R.bits == 16 ? SI_ALN16 : SI_ALN32] += 1; st[SI_TB] += R.tbbytes;
-        if constexpr (TRACE) { A.tr_score[r] = R.best_score; A.tr_bits[r] = R.bits; A.tr_cells[r] = (long long)R.cells; }
+    if constexpr (!SEEDED) {
+        int drc;
+        if constexpr (WPL == 0) drc = dp_align32(A, S, G.N, seq, len, ring, ring_info, lane, R);
+        else drc = dp_band16<T, WPL>(A, S, tm, G.N, seq, len, reinterpret_cast<uint32_t *>(ring), R, aln);
+        if (aln && drc != ST_OK) { rc = drc; aln = false; }
+        tk0 = clock64();
+        if (aln && lane == 0) {
+            st[SI_T_DP] += tk0 - tk1;
+            st[SI_CELLS] += R.cells; st[SI_INTOPS] += R.intops; st[SI_FULL] += R.full; st[SI_ALN] += 1;
+            st[R.bits == 16 ? SI_ALN16 : SI_ALN32] += 1; st[SI_TB] += R.tbbytes;
+            if constexpr (TRACE) { A.tr_score[r] = R.best_score; A.tr_bits[r] = R.bits; A.tr_cells[r] = (long long)R.cells; }
+        }
+        tm.sync();
+        if (!tm.wany(aln)) return rc;
+        bool ok;
+        if constexpr (WPL == 0) ok = traceback<int32_t, 0, T>(A, S, tm, seq, len, R, ring, aln);
+        else ok = traceback<int16_t, 2 * WPL, T>(A, S, tm, seq, len, R, ring, aln);
+        tm.sync();
+        if (aln && !ok) { rc = ST_EMPTY; aln = false; }
+        tk1 = clock64();
+        if (aln && lane == 0) st[SI_T_TB] += tk1 - tk0;
+    } else {
+        /*
+         * `abpoa -S`: the read is aligned window by window between its anchors (exact k-mers shared
+         * with the previous read, csrc/seed.cpp).  A window = the stretch of the read before an anchor
+         * against the sub-graph between the previous anchor's last node (or the source) and the
+         * anchor's first node; the anchor k-mer itself is k forced matches onto the previous read's
+         * nodes; the last window ends at the sink.  One merge per read, as without seeding.
+         */
+        const int k = A.seed_k;
+        const int32_t *prevrow = prevrow_p(A, S);
+        int32_t *qmap = qmap_p(A, S);
+        const int a0 = aln ? A.anc_off[r] : 0, n_anc = aln ? A.anc_off[r + 1] - a0 : -1;
+        const int n_win = tm.wmax(n_anc + 1);
+        Slot V = S;
+        V.sub = 1;
+        long long score = 0;
+        unsigned long long w_cells = 0, w_intops = 0, w_full = 0, w_tb = 0;
+        int bits = 0, rb = 0, qbeg = 0;
+        for (int wi = 0; wi < n_win; ++wi) {
+            const bool won = aln && wi <= n_anc;
+            int re = G.N - 1, qend = len, t0 = 0;
+            if (won && wi < n_anc) { const int2 an = A.anc[a0 + wi]; t0 = an.x; qend = an.y; re = prevrow[t0]; }
+            const int ql = qend - qbeg;
+            bool run = won && ql > 0;
+            if (tm.wany(run)) {
+                const int Ns = extract_window<T>(A, S, tm, rb, re, run);
+                if (run && Ns < 2) { rc = ST_EMPTY; aln = false; run = false; }
+                const uint8_t *wq = seq + qbeg;
+                int drc;
+                if constexpr (WPL == 0) drc = run ? dp_align32(A, V, Ns, wq, ql, ring, ring_info, lane, R) : ST_OK;
+                else drc = dp_band16<T, WPL>(A, V, tm, Ns, wq, ql, reinterpret_cast<uint32_t *>(ring), R, run);
+                if (run && drc != ST_OK) { rc = drc; aln = false; run = false; }
+                tm.sync();
+                bool ok;
+                if constexpr (WPL == 0) ok = traceback<int32_t, 0, T>(A, V, tm, wq, ql, R, ring, run);
+                else ok = traceback<int16_t, 2 * WPL, T>(A, V, tm, wq, ql, R, ring, run);
+                tm.sync();
+                if (run && !ok) { rc = ST_EMPTY; aln = false; run = false; }
+                if (run) {
+                    score += R.best_score; bits = max(bits, R.bits);
+                    w_cells += R.cells; w_intops += R.intops; w_full += R.full; w_tb += R.tbbytes;
+                    /* rows of the view -> rows of the graph */
+                    const int32_t *vq = qmap_p(A, V), *sub2row = srcof_p(A, S);
+#pragma unroll 1
+                    for (int t = lane; t < ql; t += T) { const int sr = vq[t]; qmap[qbeg + t] = sr < 0 ? -1 : sub2row[sr]; }
+                }
+                tm.sync();
+            }
+            if (aln && wi < n_anc) {                   // the anchor k-mer: forced matches onto the previous read's nodes
+#pragma unroll 1
+                for (int j = lane; j < k; j += T) qmap[qend + j] = prevrow[t0 + j];
+                rb = prevrow[t0 + k - 1]; qbeg = qend + k;
+                score += (long long)k * A.P.match;
+            }
+        }
+        tm.sync();
+        tk0 = clock64();
+        if (aln && lane == 0) {
+            st[SI_T_DP] += tk0 - tk1;
+            st[SI_CELLS] += w_cells; st[SI_INTOPS] += w_intops; st[SI_FULL] += w_full; st[SI_ALN] += 1;
+            st[(bits == 32) ? SI_ALN32 : SI_ALN16] += 1; st[SI_TB] += w_tb;
+            if constexpr (TRACE) { A.tr_score[r] = (int)score; A.tr_bits[r] = bits ? bits : 16; A.tr_cells[r] = (long long)w_cells; }
+        }
+        tk1 = tk0;
     }
-    tm.sync();
     if (!tm.wany(aln)) return rc;
-    bool ok;
-    if constexpr (WPL == 0) ok = traceback<int32_t, 0, T>(A, S, tm, seq, len, R, ring, aln);
-    else ok = traceback<int16_t, 2 * WPL, T>(A, S, tm, seq, len, R, ring, aln);
-    tm.sync();
-    if (aln && !ok) { rc = ST_EMPTY; aln = false; }
-    tk1 = clock64();
-    if (aln && lane == 0) st[SI_T_TB] += tk1 - tk0;
-    if (!tm.wany(aln)) return rc;
-    const int mrc = merge_read<T>(A, S, tm, G.par, G.N, G.E, seq, len, creator0, tr_aln, tr_node, aln);
+    const int mrc = merge_read<T, SEEDED>(A, S, tm, G.par, G.N, G.E, seq, len, creator0, tr_aln, tr_node, aln);
     if (aln && mrc != ST_OK) rc = mrc;
     if (aln && lane == 0) st[SI_T_MERGE] += clock64() - tk1;
     return rc;
@@ -202,7 +269,7 @@ __host__ __device__ constexpr int min_blocks() {
  * teams of a warp run it in lockstep (see Team): a team without work idles by predicate until the
  * other one is done as well.
  */
-template <int T, int WPL, bool TRACE>
+template <int T, int WPL, bool TRACE, bool SEEDED>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (min_blocks<T, WPL>()))
 poa_group_kernel(const __grid_constant__ KernelArgs A) {
     static_assert(WPL != 0 || T == 32, "int32 lanes use the whole warp");
@@ -252,7 +319,7 @@ poa_group_kernel(const __grid_constant__ KernelArgs A) {
         }
         if (!tm.wany(G.g >= 0)) break;
         const bool act = G.g >= 0 && G.r < G.r1;
-        int rc = read_step<T, WPL, TRACE>(A, tm, slot, G, act, ring, ring_info, gst);
+        int rc = read_step<T, WPL, TRACE, SEEDED>(A, tm, slot, G, act, ring, ring_info, gst);
         if (G.g >= 0 && !act) rc = ST_EMPTY;          // a group without reads
         const bool fin = G.g >= 0 && rc == ST_PENDING && G.r == G.r1;
         if (tm.wany(fin)) {
@@ -336,21 +403,24 @@ cudaError_t launch_gather(const uint8_t *cons, const int64_t *region_off, const 
 }
 
 template <int T, int WPL>
-static const void *variant_fn(bool trace) {
-    return trace ? reinterpret_cast<const void *>(&poa_group_kernel<T, WPL, true>) : reinterpret_cast<const void *>(&poa_group_kernel<T, WPL, false>);
+static const void *variant_fn(bool trace, bool seeded) {
+    if (seeded) return trace ? reinterpret_cast<const void *>(&poa_group_kernel<T, WPL, true, true>)
+                             : reinterpret_cast<const void *>(&poa_group_kernel<T, WPL, false, true>);
+    return trace ? reinterpret_cast<const void *>(&poa_group_kernel<T, WPL, true, false>)
+                 : reinterpret_cast<const void *>(&poa_group_kernel<T, WPL, false, false>);
 }
 
 /* the instantiated kernel variants: (team size, words per lane) */
 #define MPOA_FOR_VARIANTS(X) X(32, 2) X(32, 4) X(32, 8) X(32, 0)
 
-static const void *kernel_of(int code, bool trace) {
-#define X(T, W) if (code == variant_code(T, W)) return variant_fn<T, W>(trace);
+static const void *kernel_of(int code, bool trace, bool seeded) {
+#define X(T, W) if (code == variant_code(T, W)) return variant_fn<T, W>(trace, seeded);
     MPOA_FOR_VARIANTS(X)
 #undef X
     return nullptr;
 }
 
-bool variant_exists(int code) { return kernel_of(code, false) != nullptr; }
+bool variant_exists(int code) { return kernel_of(code, false, false) != nullptr; }
 
 size_t poa_smem_bytes(int code, int wcap, int warps_per_block) {
 #define X(T, W) if (code == variant_code(T, W)) return ((size_t)warps_per_block * (32 / T) * team_words<T, W>(wcap) + warps_per_block * 32) * sizeof(int);
@@ -361,7 +431,7 @@ size_t poa_smem_bytes(int code, int wcap, int warps_per_block) {
 
 cudaError_t launch_poa(int code, const KernelArgs &A, int n_blocks, int warps_per_block, cudaStream_t stream) {
     const size_t smem = poa_smem_bytes(code, A.wcap, warps_per_block);
-    const void *fn = kernel_of(code, A.tr_aln != nullptr);   // all five trace arrays are set together
+    const void *fn = kernel_of(code, A.tr_aln != nullptr, A.anc_off != nullptr);   // all five trace arrays are set together
     if (!fn) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -369,10 +439,10 @@ cudaError_t launch_poa(int code, const KernelArgs &A, int n_blocks, int warps_pe
     return cudaLaunchKernel(fn, dim3(n_blocks), dim3(warps_per_block * 32), args, smem, stream);
 }
 
-int poa_max_blocks_per_sm(int code, int wcap, int warps_per_block) {
+int poa_max_blocks_per_sm(int code, int wcap, int warps_per_block, bool seeded) {
     int nb = 0;
     const size_t smem = poa_smem_bytes(code, wcap, warps_per_block);
-    const void *fn = kernel_of(code, false);
+    const void *fn = kernel_of(code, false, seeded);
     if (!fn) return 0;
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, warps_per_block * 32, smem) != cudaSuccess) return 0;

@@ -1,0 +1,175 @@
+/*
+ * seed.cpp -- host side of `abpoa -S` (reference utils/SpliceDefineConsensus.py:916-919: median read
+ * length >= 8000): the anchors of every read of a seeded group against the read before it.
+ *
+ * abPOA's seeding (upstream abpoa_seed.c, not available here) is summarised in SURVEY.md A.10:
+ * (k = 19, w = 10) minimizers, hits between consecutive reads, colinear chaining, anchors at least
+ * 500 nt apart.  The rules this library implements (include/mandalorion_poa.h, "Seeded groups"):
+ *   minimizers  forward strand, minimap2 sampling rule (ties of a window all reported), N restarts
+ *   hits        equal k-mer hash in read i-1 and read i; a hash that occurs more than 8 times in
+ *               read i-1 is ignored; order (position in read i-1, position in read i)
+ *   chain       best colinear chain over the 64 previous hits, diagonal drift <= 100, a step scores
+ *               min(k, advance); first maximum wins
+ *   anchors     along the chain, keep a hit whose k-mer starts >= 500 nt after the end of the last
+ *               kept one (or the read start) on both reads
+ * The kernels (poa_seed.cuh) turn every anchor into k forced matches and align the stretches between
+ * anchors to the sub-graph between the anchor nodes.
+ */
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <thread>
+#include <vector>
+
+namespace mpoa {
+
+namespace {
+
+struct KmerAt { uint64_t h; int32_t end; };
+
+inline uint64_t hash_kmer(uint64_t x, uint64_t mask) {
+    x = (~x + (x << 21)) & mask;
+    x ^= x >> 24;
+    x = (x + (x << 3) + (x << 8)) & mask;
+    x ^= x >> 14;
+    x = (x + (x << 2) + (x << 4)) & mask;
+    x ^= x >> 28;
+    x = (x + (x << 31)) & mask;
+    return x;
+}
+
+inline int code_of(uint8_t c) {
+    switch (c & 0xdf) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; default: return 4; }
+}
+
+/* forward-strand (w,k) minimizers of an ASCII read */
+void forward_minimizers(const uint8_t *s, int n, int w, int k, std::vector<KmerAt> &out) {
+    out.clear();
+    const uint64_t mask = (1ULL << (2 * k)) - 1;
+    std::vector<uint64_t> ring_h(w, UINT64_MAX);
+    std::vector<int32_t> ring_end(w, 0);
+    uint64_t word = 0, cur_min = UINT64_MAX;
+    int32_t cur_end = 0;
+    int run = 0, slot = 0, min_slot = 0;
+    auto put = [&](uint64_t h, int32_t e) { if (h != UINT64_MAX) out.push_back(KmerAt{h, e}); };
+    auto put_equal = [&](int a, int b) { for (int j = a; j < b; ++j) if (ring_h[j] == cur_min && ring_end[j] != cur_end) put(ring_h[j], ring_end[j]); };
+    for (int i = 0; i < n; ++i) {
+        const int c = code_of(s[i]);
+        uint64_t h = UINT64_MAX;
+        if (c < 4) {
+            word = ((word << 2) | (uint64_t)c) & mask;
+            if (++run >= k) h = hash_kmer(word, mask);
+        } else run = 0;
+        ring_h[slot] = h; ring_end[slot] = i;
+        if (run == w + k - 1 && cur_min != UINT64_MAX) { put_equal(slot + 1, w); put_equal(0, slot); }
+        if (h <= cur_min) {
+            if (run >= w + k) put(cur_min, cur_end);
+            cur_min = h; cur_end = i; min_slot = slot;
+        } else if (slot == min_slot) {
+            if (run >= w + k - 1) put(cur_min, cur_end);
+            uint64_t best = UINT64_MAX;
+            int where = slot;
+            for (int t = 1; t <= w; ++t) {
+                const int j = (slot + t) % w;
+                if (ring_h[j] <= best) { best = ring_h[j]; where = j; }
+            }
+            cur_min = best; cur_end = ring_end[where]; min_slot = where;
+            if (run >= w + k - 1 && cur_min != UINT64_MAX) { put_equal(slot + 1, w); put_equal(0, slot + 1); }
+        }
+        slot = slot + 1 == w ? 0 : slot + 1;
+    }
+    put(cur_min, cur_end);
+}
+
+struct Pair { int32_t t, q; };
+
+void anchors_of(const std::vector<KmerAt> &prev_sorted, const std::vector<KmerAt> &cur, int k, int min_gap,
+                std::vector<Pair> &hits, std::vector<int32_t> &score, std::vector<int32_t> &from, std::vector<int32_t> &out) {
+    hits.clear();
+    for (const KmerAt &m : cur) {
+        auto lo = std::lower_bound(prev_sorted.begin(), prev_sorted.end(), m.h, [](const KmerAt &a, uint64_t h) { return a.h < h; });
+        auto hi = lo;
+        while (hi != prev_sorted.end() && hi->h == m.h) ++hi;
+        if (hi - lo > 8) continue;
+        for (auto it = lo; it != hi; ++it) hits.push_back(Pair{it->end, m.end});
+    }
+    std::sort(hits.begin(), hits.end(), [](const Pair &a, const Pair &b) { return a.t != b.t ? a.t < b.t : a.q < b.q; });
+    const int n = (int)hits.size();
+    if (n == 0) return;
+    score.assign(n, k); from.assign(n, -1);
+    int top = 0;
+    for (int i = 0; i < n; ++i) {
+        const int first = std::max(0, i - 64);
+        for (int j = i - 1; j >= first; --j) {
+            const int dt = hits[i].t - hits[j].t, dq = hits[i].q - hits[j].q;
+            if (dt <= 0 || dq <= 0 || std::abs(dt - dq) > 100) continue;
+            const int cand = score[j] + std::min(k, std::min(dt, dq));
+            if (cand > score[i]) { score[i] = cand; from[i] = j; }
+        }
+        if (score[i] > score[top]) top = i;
+    }
+    std::vector<int32_t> path;
+    for (int i = top; i >= 0; i = from[i]) path.push_back(i);
+    int32_t end_t = -1, end_q = -1;
+    for (auto it = path.rbegin(); it != path.rend(); ++it) {
+        const int32_t t0 = hits[*it].t - k + 1, q0 = hits[*it].q - k + 1;
+        if (t0 - (end_t + 1) >= min_gap && q0 - (end_q + 1) >= min_gap) {
+            out.push_back(t0); out.push_back(q0);
+            end_t = hits[*it].t; end_q = hits[*it].q;
+        }
+    }
+}
+
+}  // namespace
+
+/*
+ * Anchors of every read of the flagged groups: anc_off[n_reads + 1] (prefix counts of anchors),
+ * anc = (start in the previous read, start in this read) pairs.  Unflagged groups and first reads
+ * have none.  n_threads host threads over groups.
+ */
+void seed_batch(int64_t n_groups, const int64_t *gro, const int64_t *rbo, const uint8_t *bases, const uint8_t *flags,
+                int k, int w, int min_gap, int n_threads, std::vector<int32_t> &anc_off, std::vector<int32_t> &anc) {
+    const int64_t n_reads = n_groups > 0 ? gro[n_groups] : 0;
+    std::vector<std::vector<int32_t>> per_read((size_t)n_reads);
+    std::atomic<int64_t> next(0);
+    auto worker = [&]() {
+        std::vector<KmerAt> a, b;
+        std::vector<Pair> hits;
+        std::vector<int32_t> score, from;
+        for (;;) {
+            const int64_t g = next.fetch_add(1);
+            if (g >= n_groups) break;
+            if (!flags || !(flags[g] & 1)) continue;
+            std::vector<KmerAt> *prev = &a, *cur = &b;
+            int64_t prev_r = -1;
+            for (int64_t r = gro[g]; r < gro[g + 1]; ++r) {
+                const int len = (int)(rbo[r + 1] - rbo[r]);
+                if (len <= 0) continue;                 // an empty read is skipped by the aligner too
+                forward_minimizers(bases + rbo[r], len, w, k, *cur);
+                if (prev_r >= 0) {
+                    /* *prev is already sorted by hash */
+                    anchors_of(*prev, *cur, k, min_gap, hits, score, from, per_read[(size_t)r]);
+                }
+                std::sort(cur->begin(), cur->end(), [](const KmerAt &x, const KmerAt &y) { return x.h != y.h ? x.h < y.h : x.end < y.end; });
+                std::swap(prev, cur);
+                prev_r = r;
+            }
+        }
+    };
+    int nt = std::max(1, n_threads);
+    if ((int64_t)nt > n_groups) nt = (int)std::max<int64_t>(1, n_groups);
+    if (nt <= 1) worker();
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(worker);
+        for (auto &t : th) t.join();
+    }
+    anc_off.assign((size_t)n_reads + 1, 0);
+    anc.clear();
+    for (int64_t r = 0; r < n_reads; ++r) {
+        anc.insert(anc.end(), per_read[(size_t)r].begin(), per_read[(size_t)r].end());
+        anc_off[(size_t)r + 1] = (int32_t)(anc.size() / 2);
+    }
+}
+
+}  // namespace mpoa

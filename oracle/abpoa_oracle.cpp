@@ -458,10 +458,13 @@ void align_to_graph(Graph &g, const Par &P, const uint8_t *q, int qlen, DpScratc
 }
 
 /* upstream abpoa_graph.c: abpoa_add_graph_sequence() -- first read, linear chain (A.3) */
-void add_sequence(Graph &g, const uint8_t *seq, int len, int creator0, int32_t *base_aln, int32_t *base_node) {
+void add_sequence(Graph &g, const uint8_t *seq, int len, int creator0, int32_t *base_aln, int32_t *base_node,
+                  std::vector<int> *qnode = nullptr) {
     int last = SRC;
+    if (qnode) qnode->assign(len, -1);
     for (int i = 0; i < len; ++i) {
         int cur = add_node(g, seq[i], creator0 + i);
+        if (qnode) (*qnode)[i] = cur;
         add_edge(g, last, cur, 0, 1);
         last = cur;
         if (base_aln) base_aln[i] = -1;
@@ -473,8 +476,9 @@ void add_sequence(Graph &g, const uint8_t *seq, int len, int creator0, int32_t *
 
 /* upstream abpoa_graph.c: abpoa_add_subgraph_alignment() over the whole graph (A.8) */
 void add_alignment(Graph &g, const uint8_t *seq, int len, const std::vector<Cig> &cigar, int creator0,
-                   int32_t *base_aln, int32_t *base_node) {
+                   int32_t *base_aln, int32_t *base_node, std::vector<int> *qnode = nullptr) {
     int last_id = SRC, last_new = 0, query_id = -1;
+    if (qnode) qnode->assign(len, -1);
     for (const Cig &c : cigar) {
         if (c.op == 0) {
             ++query_id;
@@ -496,6 +500,7 @@ void add_alignment(Graph &g, const uint8_t *seq, int len, const std::vector<Cig>
                 last_id = node_id; last_new = 0;
             }
             if (base_node) base_node[query_id] = g.node[last_id].creator;
+            if (qnode) (*qnode)[query_id] = last_id;
         } else if (c.op == 1) {
             ++query_id;
             int new_id = add_node(g, seq[query_id], creator0 + query_id);
@@ -503,6 +508,7 @@ void add_alignment(Graph &g, const uint8_t *seq, int len, const std::vector<Cig>
             last_id = new_id; last_new = 1;
             if (base_aln) base_aln[query_id] = -1;
             if (base_node) base_node[query_id] = creator0 + query_id;
+            if (qnode) (*qnode)[query_id] = new_id;
         }
     }
     (void)len;
@@ -566,9 +572,198 @@ struct GroupOut {
     mpoa_stats st;
 };
 
+/* ------------------------------------------------------------------------------------------ */
+/* `abpoa -S`: minimizer-seeded, windowed alignment (upstream abpoa_seed.c + abpoa_anchor_poa in  */
+/* abpoa.c).  LOW-CONFIDENCE restatement: the upstream source is unavailable, the structure below  */
+/* follows SURVEY.md A.10 -- (k,w) minimizers of consecutive reads, colinear chaining of their     */
+/* hits, anchors at least min_w apart, every anchor k-mer a forced run of matches, the stretches   */
+/* between anchors aligned to the sub-graph between the anchor nodes -- and every constant that   */
+/* the summary does not pin (chaining band, look-back, tie rules) is OUR choice, documented here:  */
+/*   minimizers  forward strand only, minimap2 sampling rule, invertible 64-bit mix of the k-mer  */
+/*   hits        equal hash in read i-1 (target) and read i (query); hashes with more than        */
+/*               8 occurrences in the target are ignored; sorted by (target pos, query pos)        */
+/*   chain       f[i] = k + max over the 64 previous hits j with 0 < dt, 0 < dq, |dt-dq| <= 100    */
+/*               of f[j] - k + min(k, dt, dq); best chain = first maximum of f                    */
+/*   anchors     walk the chain left to right, keep a hit when its k-mer starts >= min_w after the */
+/*               end of the last kept one (or the read start) on BOTH reads                        */
+/*   sub-graph   the nodes that lie on a path from the begin node to the end node (both ends act   */
+/*               as source / sink of an ordinary alignment; remain = global remain - remain[end]-1)*/
+/* The product library implements the same rules independently (csrc/seed.cpp + the kernels).       */
+/* ------------------------------------------------------------------------------------------ */
+
+inline uint64_t mix64(uint64_t key, uint64_t mask) {
+    key = (~key + (key << 21)) & mask;
+    key = key ^ key >> 24;
+    key = ((key + (key << 3)) + (key << 8)) & mask;
+    key = key ^ key >> 14;
+    key = ((key + (key << 2)) + (key << 4)) & mask;
+    key = key ^ key >> 28;
+    key = (key + (key << 31)) & mask;
+    return key;
+}
+
+struct Mz { uint64_t key; int pos; };   // pos = last base of the k-mer
+
+/* (w,k) minimizers of the forward strand of nt4 codes (4 = N restarts the window) */
+void minimizers_fw(const uint8_t *s, int len, int w, int k, std::vector<Mz> &out) {
+    out.clear();
+    if (w <= 0 || w > 64 || k <= 0 || k > 28) return;
+    const uint64_t mask = (1ULL << 2 * k) - 1;
+    uint64_t fw = 0;
+    std::vector<uint64_t> bkey(w, UINT64_MAX);
+    std::vector<int> bpos(w, 0);
+    uint64_t mkey = UINT64_MAX;
+    int mpos = 0, l = 0, bp = 0, mp = 0;
+    auto emit = [&](uint64_t key, int pos) { if (key != UINT64_MAX) out.push_back(Mz{key, pos}); };
+    auto ties = [&](int from, int to) { for (int j = from; j < to; ++j) if (bkey[j] == mkey && bpos[j] != mpos) emit(bkey[j], bpos[j]); };
+    for (int i = 0; i < len; ++i) {
+        const int c = s[i];
+        uint64_t ckey = UINT64_MAX;
+        if (c < 4) {
+            fw = (fw << 2 | (uint64_t)c) & mask;
+            ++l;
+            if (l >= k) ckey = mix64(fw, mask);
+        } else l = 0;
+        bkey[bp] = ckey; bpos[bp] = i;
+        if (l == w + k - 1 && mkey != UINT64_MAX) { ties(bp + 1, w); ties(0, bp); }
+        if (ckey <= mkey) {
+            if (l >= w + k) emit(mkey, mpos);
+            mkey = ckey; mpos = i; mp = bp;
+        } else if (bp == mp) {
+            if (l >= w + k - 1) emit(mkey, mpos);
+            uint64_t best = UINT64_MAX;
+            int bj = bp;
+            for (int t = 1; t <= w; ++t) {
+                int j = bp + t; if (j >= w) j -= w;
+                if (bkey[j] <= best) { best = bkey[j]; bj = j; }
+            }
+            mkey = best; mpos = bpos[bj]; mp = bj;
+            if (l >= w + k - 1 && mkey != UINT64_MAX) { ties(bp + 1, w); ties(0, bp + 1); }
+        }
+        if (++bp == w) bp = 0;
+    }
+    emit(mkey, mpos);
+}
+
+/* anchors (start in the previous read, start in this read) of the seeded alignment of `cur` */
+void seed_anchors(const uint8_t *prev, int plen, const uint8_t *cur, int clen, int k, int w, int min_w,
+                  std::vector<std::pair<int, int>> &anchors) {
+    anchors.clear();
+    std::vector<Mz> mt, mq;
+    minimizers_fw(prev, plen, w, k, mt);
+    minimizers_fw(cur, clen, w, k, mq);
+    std::sort(mt.begin(), mt.end(), [](const Mz &a, const Mz &b) { return a.key != b.key ? a.key < b.key : a.pos < b.pos; });
+    struct Hit { int t, q; };
+    std::vector<Hit> h;
+    for (const Mz &m : mq) {
+        auto lo = std::lower_bound(mt.begin(), mt.end(), m.key, [](const Mz &a, uint64_t key) { return a.key < key; });
+        auto hi = lo;
+        while (hi != mt.end() && hi->key == m.key) ++hi;
+        if (hi - lo > 8) continue;
+        for (auto it = lo; it != hi; ++it) h.push_back(Hit{it->pos, m.pos});
+    }
+    std::sort(h.begin(), h.end(), [](const Hit &a, const Hit &b) { return a.t != b.t ? a.t < b.t : a.q < b.q; });
+    const int n = (int)h.size();
+    if (n == 0) return;
+    std::vector<int> f(n), p(n);
+    int best = 0;
+    for (int i = 0; i < n; ++i) {
+        f[i] = k; p[i] = -1;
+        for (int j = i - 1; j >= 0 && j >= i - 64; --j) {
+            const int dt = h[i].t - h[j].t, dq = h[i].q - h[j].q;
+            if (dt <= 0 || dq <= 0) continue;
+            const int dd = dt > dq ? dt - dq : dq - dt;
+            if (dd > 100) continue;
+            const int sc = f[j] + std::min(k, std::min(dt, dq));
+            if (sc > f[i]) { f[i] = sc; p[i] = j; }
+        }
+        if (f[i] > f[best]) best = i;
+    }
+    std::vector<int> chain;
+    for (int i = best; i >= 0; i = p[i]) chain.push_back(i);
+    std::reverse(chain.begin(), chain.end());
+    int last_t = -1, last_q = -1;   // last base of the last kept anchor
+    for (int i : chain) {
+        const int t0 = h[i].t - k + 1, q0 = h[i].q - k + 1;
+        if (t0 - (last_t + 1) >= min_w && q0 - (last_q + 1) >= min_w) {
+            anchors.emplace_back(t0, q0);
+            last_t = h[i].t; last_q = h[i].q;
+        }
+    }
+}
+
+/* alignment of query[0..ql) to the sub-graph of the nodes on a path beg -> end (both exclusive in the
+ * cigar: beg plays the source, end the sink).  Appends the cigar (global node ids, query index + qoff). */
+bool align_to_subgraph(Graph &g, const Par &P, int beg_id, int end_id, const uint8_t *q, int ql, int qoff, DpScratch &S,
+                       AlnOut &R, std::vector<Cig> &cigar, int64_t &score_sum) {
+    if (ql <= 0) return true;
+    const int n = g.node_n();
+    std::vector<char> fw(n, 0), bw(n, 0);
+    std::vector<int> stack;
+    stack.push_back(beg_id); fw[beg_id] = 1;
+    while (!stack.empty()) { int v = stack.back(); stack.pop_back(); for (int u : g.node[v].out_id) if (!fw[u]) { fw[u] = 1; stack.push_back(u); } }
+    stack.push_back(end_id); bw[end_id] = 1;
+    while (!stack.empty()) { int v = stack.back(); stack.pop_back(); for (int u : g.node[v].in_id) if (!bw[u]) { bw[u] = 1; stack.push_back(u); } }
+    if (!fw[end_id]) return false;
+    std::vector<int> sub_of(n, -1), glob;
+    glob.push_back(beg_id); glob.push_back(end_id);
+    sub_of[beg_id] = SRC; sub_of[end_id] = SINK;
+    for (int v = 0; v < n; ++v)
+        if (fw[v] && bw[v] && v != beg_id && v != end_id) { sub_of[v] = (int)glob.size(); glob.push_back(v); }
+    Graph sg;
+    sg.node.resize(glob.size());
+    for (size_t s2 = 0; s2 < glob.size(); ++s2) {
+        const Node &src = g.node[glob[s2]];
+        Node &d = sg.node[s2];
+        d.base = src.base; d.creator = src.creator;
+        if ((int)s2 != SINK)
+            for (size_t e = 0; e < src.out_id.size(); ++e)
+                if (sub_of[src.out_id[e]] >= 0) { d.out_id.push_back(sub_of[src.out_id[e]]); d.out_w.push_back(src.out_w[e]); }
+        if ((int)s2 != SRC)
+            for (int u : src.in_id) if (sub_of[u] >= 0) d.in_id.push_back(sub_of[u]);
+        if ((int)s2 != SRC && (int)s2 != SINK)
+            for (int a : src.aligned) if (sub_of[a] >= 0) d.aligned.push_back(sub_of[a]);
+    }
+    if (!topological_sort(sg)) return false;
+    for (size_t s2 = 0; s2 < glob.size(); ++s2)
+        sg.max_remain[s2] = g.max_remain[glob[s2]] - g.max_remain[end_id] - 1;
+    AlnOut W;
+    align_to_graph(sg, P, q, ql, S, W);
+    R.band_cells += W.band_cells; R.int_ops += W.int_ops; R.full_cells += W.full_cells;
+    R.max_width = std::max(R.max_width, W.max_width);
+    R.bits = std::max(R.bits, W.bits);
+    if (!W.ok) return false;
+    score_sum += W.best_score;
+    for (const Cig &c : W.cigar) cigar.push_back(Cig{c.op, c.node_id >= 0 ? glob[c.node_id] : -1, c.qidx + qoff});
+    return true;
+}
+
+/* upstream abpoa.c: abpoa_anchor_poa() for one read */
+void align_seeded(Graph &g, const Par &P, const uint8_t *seq, int len, const uint8_t *prev, int plen,
+                  const std::vector<int> &prev_node, DpScratch &S, AlnOut &R) {
+    const int k = P.opt.seed_k > 0 ? P.opt.seed_k : 19, w = P.opt.seed_w > 0 ? P.opt.seed_w : 10;
+    const int min_w = P.opt.seed_min_w > 0 ? P.opt.seed_min_w : 500;
+    std::vector<std::pair<int, int>> anchors;
+    seed_anchors(prev, plen, seq, len, k, w, min_w, anchors);
+    R.ok = false; R.cigar.clear(); R.bits = 0;
+    int64_t score = 0;
+    int beg_id = SRC, beg_q = 0;
+    for (const auto &a : anchors) {
+        const int t0 = a.first, q0 = a.second;
+        if (!align_to_subgraph(g, P, beg_id, prev_node[t0], seq + beg_q, q0 - beg_q, beg_q, S, R, R.cigar, score)) return;
+        for (int j = 0; j < k; ++j) R.cigar.push_back(Cig{0, prev_node[t0 + j], q0 + j});
+        score += (int64_t)k * P.match;
+        beg_id = prev_node[t0 + k - 1]; beg_q = q0 + k;
+    }
+    if (!align_to_subgraph(g, P, beg_id, SINK, seq + beg_q, len - beg_q, beg_q, S, R, R.cigar, score)) return;
+    R.best_score = (int)score;
+    if (R.bits == 0) R.bits = 16;
+    R.ok = true;
+}
+
 /* upstream abpoa.c: abpoa_msa1() -> abpoa_poa() -> abpoa_output(), seeding disabled */
 void run_group(const Par &P, int64_t r0, int64_t r1, const int64_t *read_base_off, const uint8_t *bases,
-               mpoa_trace *tr, GroupOut &out) {
+               mpoa_trace *tr, GroupOut &out, bool seeded) {
     std::memset(&out.st, 0, sizeof(out.st));
     out.st.n_groups = 1;
     out.st.n_reads = r1 - r0;
@@ -578,7 +773,10 @@ void run_group(const Par &P, int64_t r0, int64_t r1, const int64_t *read_base_of
     Graph g;
     DpScratch S;
     AlnOut R;
-    std::vector<uint8_t> seq;
+    std::vector<uint8_t> seq, prev_seq;
+    std::vector<int> prev_node, cur_node;
+    out.st.n_seed_groups = seeded ? 1 : 0;
+    out.st.n_seed_applied = seeded ? 1 : 0;
     const int64_t gbase = read_base_off[r0];
     for (int64_t r = r0; r < r1; ++r) {
         const int64_t b0 = read_base_off[r], b1 = read_base_off[r + 1];
@@ -593,14 +791,16 @@ void run_group(const Par &P, int64_t r0, int64_t r1, const int64_t *read_base_of
         if (g.node_n() == 2) {
             /* abpoa_add_graph_sequence dies on an empty first read -> no output at all */
             if (len <= 0) return;
-            add_sequence(g, seq.data(), len, (int)(b0 - gbase), baln, bnode);
+            add_sequence(g, seq.data(), len, (int)(b0 - gbase), baln, bnode, &prev_node);
+            prev_seq = seq;
             continue;
         }
         if (len <= 0) continue;  // abpoa_align_sequence_to_graph returns early, nothing is added
         if (!g.sorted && !topological_sort(g)) return;
         R.band_cells = R.int_ops = R.full_cells = 0;
         R.max_width = 0;
-        align_to_graph(g, P, seq.data(), len, S, R);
+        if (seeded) align_seeded(g, P, seq.data(), len, prev_seq.data(), (int)prev_seq.size(), prev_node, S, R);
+        else align_to_graph(g, P, seq.data(), len, S, R);
         out.st.n_alignments++;
         out.st.band_cells += R.band_cells;
         out.st.int_ops += R.int_ops;
@@ -611,7 +811,9 @@ void run_group(const Par &P, int64_t r0, int64_t r1, const int64_t *read_base_of
         if (tr && tr->read_bits) tr->read_bits[r] = R.bits;
         if (tr && tr->read_band_cells) tr->read_band_cells[r] = R.band_cells;
         if (!R.ok) return;  // abpoa exits -> empty consensus file -> reference falls back
-        add_alignment(g, seq.data(), len, R.cigar, (int)(b0 - gbase), baln, bnode);
+        add_alignment(g, seq.data(), len, R.cigar, (int)(b0 - gbase), baln, bnode, &cur_node);
+        prev_node.swap(cur_node);
+        prev_seq = seq;
     }
     if (g.node_n() <= 2) return;
     if (heaviest_bundling(g, P, out.cons)) out.status = MPOA_GROUP_OK;
@@ -634,6 +836,8 @@ extern "C" void mpoa_oracle_default_opts(mpoa_oracle_opts *o) {
     o->single_argmax = 0;
     o->hb_tie_later_wins = 1;
     o->n_threads = 1;
+    o->seed_k = 19; o->seed_w = 10; o->seed_min_w = 500;
+    o->honour_seed_flag = 1;
 }
 
 extern "C" int mpoa_oracle_consensus_batch(const mpoa_params *p, const mpoa_oracle_opts *o, int64_t n_groups,
@@ -641,7 +845,6 @@ extern "C" int mpoa_oracle_consensus_batch(const mpoa_params *p, const mpoa_orac
                                            const uint8_t *bases, const uint8_t *group_flags, int64_t *cons_off,
                                            uint8_t *cons_buf, int64_t cons_cap, int32_t *group_status,
                                            mpoa_stats *stats, mpoa_trace *trace) {
-    (void)group_flags;  // -S (seeding) is not restated: the unseeded path is run for every group
     if (!p || n_groups < 0 || (n_groups > 0 && (!group_read_off || !read_base_off || !cons_off))) return MPOA_EINVAL;
     Par P;
     P.match = p->match < 0 ? -p->match : p->match;
@@ -652,6 +855,9 @@ extern "C" int mpoa_oracle_consensus_batch(const mpoa_params *p, const mpoa_orac
     P.pn16 = p->simd_pn_i16 > 0 ? p->simd_pn_i16 : 16;
     P.pn32 = p->simd_pn_i32 > 0 ? p->simd_pn_i32 : 8;
     if (o) P.opt = *o; else mpoa_oracle_default_opts(&P.opt);
+    if (P.opt.seed_k <= 0) P.opt.seed_k = 19;
+    if (P.opt.seed_w <= 0) P.opt.seed_w = 10;
+    if (P.opt.seed_min_w <= 0) P.opt.seed_min_w = 500;
     make_matrix(P);
 
     std::vector<GroupOut> outs((size_t)n_groups);
@@ -662,7 +868,8 @@ extern "C" int mpoa_oracle_consensus_batch(const mpoa_params *p, const mpoa_orac
         for (;;) {
             int64_t gidx = next.fetch_add(1);
             if (gidx >= n_groups) break;
-            run_group(P, group_read_off[gidx], group_read_off[gidx + 1], read_base_off, bases, trace, outs[gidx]);
+            const bool seeded = group_flags && (group_flags[gidx] & MPOA_FLAG_SEED) && P.opt.honour_seed_flag;
+            run_group(P, group_read_off[gidx], group_read_off[gidx + 1], read_base_off, bases, trace, outs[gidx], seeded);
         }
     };
     if (nt <= 1) worker();

@@ -34,7 +34,13 @@ typedef struct mpoa_oracle_opts {
     int32_t hb_tie_later_wins;   /* 1: heaviest-bundling tie -> later edge if its score
                                     is >= (default 1)                                     */
     int32_t n_threads;           /* worker threads over groups, <=1: serial               */
-    int32_t reserved[4];
+    /* `abpoa -S` (groups flagged MPOA_FLAG_SEED): minimizer seeding constants, 0 = default.
+     * Restated with LOW confidence (upstream abpoa_seed.c is not available), see abpoa_oracle.cpp */
+    int32_t seed_k;              /* minimizer k-mer (default 19)                          */
+    int32_t seed_w;              /* minimizer window (default 10)                         */
+    int32_t seed_min_w;          /* minimum distance between kept anchors (default 500)   */
+    int32_t honour_seed_flag;    /* 1 (default): flagged groups run the seeded path; 0: the
+                                    flag is ignored (the unseeded algorithm for everyone)  */
 } mpoa_oracle_opts;
 
 void mpoa_oracle_default_opts(mpoa_oracle_opts *o);

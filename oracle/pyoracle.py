@@ -24,7 +24,8 @@ class _Params(C.Structure):
 
 class _Opts(C.Structure):
     _fields_ = [("clamp_end_to_pred", C.c_int32), ("single_argmax", C.c_int32), ("hb_tie_later_wins", C.c_int32),
-                ("n_threads", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("n_threads", C.c_int32), ("seed_k", C.c_int32), ("seed_w", C.c_int32), ("seed_min_w", C.c_int32),
+                ("honour_seed_flag", C.c_int32)]
 
 
 class _Stats(C.Structure):
@@ -58,6 +59,10 @@ class OracleParams:
     clamp_end_to_pred: int = 1
     single_argmax: int = 0
     hb_tie_later_wins: int = 1
+    seed_k: int = 19                # `abpoa -S` constants (groups flagged MPOA_FLAG_SEED), low-confidence restatement
+    seed_w: int = 10
+    seed_min_w: int = 500
+    honour_seed_flag: int = 1
 
 
 def build_oracle(force=False):
@@ -98,7 +103,7 @@ def pack_groups(groups):
     return gro, rbo, bases
 
 
-def oracle_consensus_batch(groups=None, packed=None, params=None, n_threads=1, trace=False):
+def oracle_consensus_batch(groups=None, packed=None, params=None, n_threads=1, trace=False, flags=None):
     """Run the oracle.  Returns dict(cons=[bytes], status=np.int32[], stats=dict, trace=dict|None)."""
     lib = _load()
     p = params or OracleParams()
@@ -107,7 +112,10 @@ def oracle_consensus_batch(groups=None, packed=None, params=None, n_threads=1, t
     nreads, nbases = len(rbo) - 1, int(rbo[-1]) if len(rbo) else 0
     cp = _Params(p.match, p.mismatch, p.gap_open1, p.gap_ext1, p.gap_open2, p.gap_ext2, p.wb, p.wf,
                  p.simd_pn_i16, p.simd_pn_i32)
-    co = _Opts(p.clamp_end_to_pred, p.single_argmax, p.hb_tie_later_wins, int(n_threads))
+    co = _Opts(p.clamp_end_to_pred, p.single_argmax, p.hb_tie_later_wins, int(n_threads), p.seed_k, p.seed_w, p.seed_min_w,
+               p.honour_seed_flag)
+    if flags is not None:
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
     # a consensus is a path in the graph, so it can never be longer than the bases of its group
     cap = max(16, nbases)
     cons_buf = np.zeros(cap, dtype=np.uint8)
@@ -124,7 +132,8 @@ def oracle_consensus_batch(groups=None, packed=None, params=None, n_threads=1, t
                       ("read_score", "read_bits", "read_band_cells", "base_aln", "base_node")])
     rc = lib.mpoa_oracle_consensus_batch(
         C.byref(cp), C.byref(co), C.c_int64(ng), gro.ctypes.data_as(C.c_void_p), rbo.ctypes.data_as(C.c_void_p),
-        bases.ctypes.data_as(C.c_void_p), None, cons_off.ctypes.data_as(C.c_void_p),
+        bases.ctypes.data_as(C.c_void_p), flags.ctypes.data_as(C.c_void_p) if flags is not None else None,
+        cons_off.ctypes.data_as(C.c_void_p),
         cons_buf.ctypes.data_as(C.c_void_p), C.c_int64(cap), status.ctypes.data_as(C.c_void_p), C.byref(st),
         C.byref(tr) if tr is not None else None)
     if rc != 0:

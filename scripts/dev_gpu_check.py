@@ -11,12 +11,12 @@ from mandalorion_b200.synth import make_groups, GroupConfig  # noqa: E402
 from oracle import oracle_consensus_batch  # noqa: E402
 
 
-def compare(groups, label, ctx, verbose=True):
+def compare(groups, label, ctx, verbose=True, flags=None):
     packed = pack_groups(groups)
     t0 = time.time()
-    o = oracle_consensus_batch(packed=packed, trace=True, n_threads=8)
+    o = oracle_consensus_batch(packed=packed, trace=True, n_threads=8, flags=flags)
     t1 = time.time()
-    g = ctx.consensus_batch(packed=packed, trace=True)
+    g = ctx.consensus_batch(packed=packed, trace=True, flags=flags)
     t2 = time.time()
     gro, rbo, _ = packed
     nbad = 0
@@ -79,6 +79,15 @@ def main():
     junk = [["".join(rng.choice(list("ACGT"), size=int(rng.integers(5, 120)))) for _ in range(int(rng.integers(2, 8)))]
             for _ in range(64)]
     bad += compare(junk, "junk", ctx)
+    if len(sys.argv) > 1 and sys.argv[1] == "seeded":
+        bad = 0
+        for name, n in (("cfg1", 32), ("cfg2", 24), ("cfg3", 8), ("cfg4", 2)):
+            gs = make_groups(name, n)
+            bad += compare(gs, name + "-S", ctx, flags=np.ones(len(gs), np.uint8))
+        mixed = make_groups("cfg1", 8) + make_groups("cfg3", 4)
+        bad += compare(mixed, "mixed-S", ctx, flags=(np.arange(len(mixed)) % 2).astype(np.uint8))
+        print("TOTAL BAD", bad)
+        return 1 if bad else 0
     if len(sys.argv) > 1 and sys.argv[1] == "big":
         bad += compare(make_groups("cfg2", 64), "cfg2", ctx)
         bad += compare(make_groups("cfg4", 8), "cfg4", ctx)

@@ -12,11 +12,11 @@ from oracle import OracleParams, oracle_consensus_batch  # noqa: E402
 
 
 def main():
-    p, _seed, path = parse_args(sys.argv[1:])
+    p, seed, path = parse_args(sys.argv[1:])
     reads = read_fasta(path)
     if not reads:
         return 0
-    out = oracle_consensus_batch([reads], params=OracleParams(match=p.match, mismatch=p.mismatch))
+    out = oracle_consensus_batch([reads], params=OracleParams(match=p.match, mismatch=p.mismatch), flags=[1 if seed else 0])
     if out["status"][0] == 0 and out["cons"][0]:
         sys.stdout.write(">Consensus_sequence\n%s\n" % out["cons"][0].decode())
     return 0

@@ -26,16 +26,19 @@ CASES = [
      dict(simd_pn_i16=8, simd_pn_i32=4)),
     ("avx512_lanes", GroupConfig("golden_e", 4, 3, 8, 120, 260, "uniform", 0.05, (0.3, 0.35, 0.35)),
      dict(simd_pn_i16=32, simd_pn_i32=16)),
+    # every group flagged MPOA_FLAG_SEED (`abpoa -S`): reads long enough for one or two anchors each
+    ("seeded_windows", GroupConfig("golden_f", 3, 3, 6, 1300, 1700, "uniform", 0.02, (0.3, 0.35, 0.35)), {}, 1),
 ]
 
 
 def main():
     out = {"provenance": "oracle/abpoa_oracle.cpp (this repo); NOT an abPOA/reference vector", "cases": []}
-    for name, cfg, pk in CASES:
+    for name, cfg, pk, *rest in CASES:
+        seed = rest[0] if rest else 0
         groups = [[r.decode() for r in g] for g in make_groups(cfg)]
-        res = oracle_consensus_batch(groups, params=OracleParams(**pk), trace=True)
+        res = oracle_consensus_batch(groups, params=OracleParams(**pk), trace=True, flags=[seed] * len(groups))
         out["cases"].append(dict(
-            name=name, params=pk, groups=groups,
+            name=name, params=pk, groups=groups, seed_flag=seed,
             consensus=[c.decode() for c in res["cons"]],
             status=[int(s) for s in res["status"]],
             read_score=[int(x) for x in res["trace"]["read_score"]],

@@ -38,7 +38,9 @@ def test_one_call_entry_point_with_host_buffers(built):
     lib = _lib()
     groups = make_groups("cfg1", 12) + [[], [b"ACGT" * 20]]
     gro, rbo, bases = pack_groups(groups)
-    want = oracle_consensus_batch(packed=(gro, rbo, bases), trace=True)
+    flags = np.zeros(len(gro) - 1, np.uint8)
+    flags[3] = 1                                                        # one group as the reference's `abpoa -S`
+    want = oracle_consensus_batch(packed=(gro, rbo, bases), trace=True, flags=flags)
     ng, nr, nb = len(gro) - 1, len(rbo) - 1, int(rbo[-1])
     h = C.c_void_p()
     par = _Params()
@@ -52,8 +54,6 @@ def test_one_call_entry_point_with_host_buffers(built):
         arrs = dict(read_score=np.zeros(nr, np.int32), read_bits=np.zeros(nr, np.int32), read_band_cells=np.zeros(nr, np.int64),
                     base_aln=np.full(nb, -9, np.int32), base_node=np.full(nb, -9, np.int32))
         tr = _Trace(*[arrs[k].ctypes.data for k in ("read_score", "read_bits", "read_band_cells", "base_aln", "base_node")])
-        flags = np.zeros(ng, np.uint8)
-        flags[3] = 1
         rc = lib.mpoa_consensus_batch(h, ng, _p(gro), _p(rbo), _p(bases), _p(flags), _p(cons_off), _p(cons_buf), nb,
                                       _p(status), C.byref(st), C.byref(tr))
         assert rc == 0, lib.mpoa_last_error(h)
@@ -61,7 +61,7 @@ def test_one_call_entry_point_with_host_buffers(built):
         got = [raw[cons_off[i]:cons_off[i + 1]] for i in range(ng)]
         assert got == want["cons"] and status.tolist() == want["status"].tolist()
         assert st.band_cells == want["stats"]["band_cells"] and st.n_alignments == want["stats"]["n_alignments"]
-        assert st.n_seed_groups == 1 and st.n_seed_applied == 0       # flagged for -S, aligned unseeded, and SAID so
+        assert st.n_seed_groups == 1 and st.n_seed_applied == 1       # flagged for -S: aligned window by window
         assert st.n_kernel_launches >= 1 and st.kernel_ms > 0 and st.h2d_ms > 0
         assert np.array_equal(arrs["read_score"], want["trace"]["read_score"])
         ok = np.repeat(np.repeat(want["status"] == 0, np.diff(gro)), np.diff(rbo))
@@ -70,12 +70,12 @@ def test_one_call_entry_point_with_host_buffers(built):
         # ---- MPOA_ENOSPC: too small an output buffer reports the need in cons_off[n_groups]; retry with it
         small = np.zeros(16, np.uint8)
         off2 = np.zeros(ng + 1, np.int64)
-        rc = lib.mpoa_consensus_batch(h, ng, _p(gro), _p(rbo), _p(bases), None, _p(off2), _p(small), 16, _p(status), None, None)
+        rc = lib.mpoa_consensus_batch(h, ng, _p(gro), _p(rbo), _p(bases), _p(flags), _p(off2), _p(small), 16, _p(status), None, None)
         assert rc == -4                                                  # MPOA_ENOSPC
         need = int(off2[ng])
         assert need == int(cons_off[ng]) > 16
         big = np.zeros(need, np.uint8)
-        rc = lib.mpoa_consensus_batch(h, ng, _p(gro), _p(rbo), _p(bases), None, _p(off2), _p(big), need, _p(status), None, None)
+        rc = lib.mpoa_consensus_batch(h, ng, _p(gro), _p(rbo), _p(bases), _p(flags), _p(off2), _p(big), need, _p(status), None, None)
         assert rc == 0 and big.tobytes() == raw[:need]
 
         # ---- argument errors come back as codes, never as crashes
@@ -100,9 +100,8 @@ def test_abpoa_compatible_executable_on_the_gpu(built, tmp_path, seed_flag):
     cmd = [os.path.join(ROOT, "bin", "abpoa-b200"), "-M", "5", "-r", "0"] + (["-S"] if seed_flag else []) + [str(fa)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stderr
-    want = oracle_consensus_batch([reads])["cons"][0].decode()
-    assert res.stdout == ">Consensus_sequence\n%s\n" % want
-    assert ("WITHOUT minimizer seeding" in res.stderr) == seed_flag      # -S is never silently accepted
+    want = oracle_consensus_batch([reads], flags=[1 if seed_flag else 0])["cons"][0].decode()
+    assert res.stdout == ">Consensus_sequence\n%s\n" % want            # -S is honoured: the seeded oracle's answer
     # an empty input file prints nothing (abpoa's soft failure; the reference falls back to the first read)
     empty = tmp_path / "empty.fasta"
     empty.write_text("")
@@ -144,18 +143,21 @@ def test_groups_that_outgrow_the_device_are_reported_not_hidden(built):
     assert pg.consensus == t
 
 
-def test_seed_flagged_groups_warn_through_the_host_layer(gpu_ctx):
-    groups = make_groups("cfg1", 2)
-    pgs = [cons_mod.PendingGroup(names=[], sequences=[r.decode() for r in g], seq_lengths=[], bypass=False, seed=(i == 0))
+def test_seed_flag_travels_through_the_host_layer(gpu_ctx):
+    """PendingGroup.seed (median length >= 8000, reference :916-919) becomes MPOA_FLAG_SEED: those groups are
+    aligned window by window between minimizer anchors, the others as a whole"""
+    groups = make_groups("cfg1", 3)
+    pgs = [cons_mod.PendingGroup(names=[], sequences=[r.decode() for r in g], seq_lengths=[], bypass=False, seed=(i != 1))
            for i, g in enumerate(groups)]
     b = cons_mod.ConsensusBatcher(gpu_ctx)
     for pg in pgs:
         b.add(pg)
-    with pytest.warns(cons_mod.SeedingNotApplied):
-        b.flush()
-    assert b.stats[0]["n_seed_groups"] == 1
-    want = oracle_consensus_batch(groups)["cons"]
-    assert [pg.consensus.encode() for pg in pgs] == want
+    b.flush()
+    assert b.stats[0]["n_seed_groups"] == 2 and b.stats[0]["n_seed_applied"] == 2
+    want = oracle_consensus_batch(groups, flags=[1, 0, 1])
+    assert [pg.consensus.encode() for pg in pgs] == want["cons"]
+    assert b.stats[0]["band_cells"] == want["stats"]["band_cells"]
+    assert b.stats[0]["band_cells"] < oracle_consensus_batch(groups)["stats"]["band_cells"]   # windows, not whole reads
 
 
 def test_dstep_with_native_orientation_on_the_gpu(gpu_ctx, tmp_path, monkeypatch):

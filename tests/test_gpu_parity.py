@@ -159,7 +159,7 @@ def test_golden_vectors(built):
         golden = json.load(fh)
     for case in golden["cases"]:
         with PoaContext(0, PoaParams(**case["params"])) as ctx:
-            got = ctx.consensus_batch(case["groups"], trace=True)
+            got = ctx.consensus_batch(case["groups"], trace=True, flags=[case.get("seed_flag", 0)] * len(case["groups"]))
         assert [c.decode() for c in got["cons"]] == case["consensus"], case["name"]
         assert [int(s) for s in got["status"]] == case["status"]
         assert [int(x) for x in got["trace"]["read_score"]] == case["read_score"]

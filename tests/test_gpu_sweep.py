@@ -56,3 +56,47 @@ def test_fuzz_lengths_depths_errors_parameters(built, seed, len_lo, spread, read
     with PoaContext(0, PoaParams(**pk)) as ctx:
         got = ctx.consensus_batch(packed=packed, trace=True)
     assert_same(got, want, packed)
+
+
+@pytest.mark.parametrize("cfg,n", [("cfg3", 24), ("cfg1", 200), ("cfg2", 96), ("cfg4", 4)])
+def test_seeded_groups_match_the_seeded_oracle(gpu_ctx, cfg, n):
+    """`abpoa -S` (MPOA_FLAG_SEED): windowed alignment between minimizer anchors.  GPU == oracle bit for bit --
+    consensus, per-read score (sum over windows + anchors), band cells, per-base nodes -- also in batches
+    that mix seeded and unseeded groups."""
+    groups = make_groups(cfg, n, first=50)
+    packed = pack_groups(groups)
+    for flags in (np.ones(n, np.uint8), (np.arange(n) % 3 == 0).astype(np.uint8)):
+        want = oracle_consensus_batch(packed=packed, trace=True, n_threads=THREADS, flags=flags)
+        got = gpu_ctx.consensus_batch(packed=packed, trace=True, flags=flags)
+        assert_same(got, want, packed)
+        assert got["stats"]["n_seed_groups"] == int(flags.sum()) == got["stats"]["n_seed_applied"]
+        plain = gpu_ctx.consensus_batch(packed=packed, flags=flags)
+        assert_same(plain, want, packed, check_trace=False)
+
+
+def test_seeded_long_reads_with_structural_differences(gpu_ctx):
+    """anchors next to long insertions / deletions, reads that share no anchor at all with their predecessor
+    (one window = the whole graph), a junk read inside a seeded group"""
+    rng = np.random.default_rng(21)
+    groups = []
+    for g in range(6):
+        t = "".join(rng.choice(list("ACGT"), 9000))
+        reads = []
+        for r in range(5):
+            s = list(t)
+            for _ in range(int(rng.integers(0, 3))):
+                pos = int(rng.integers(0, len(s) - 700))
+                if rng.random() < 0.5:
+                    del s[pos:pos + int(rng.integers(100, 600))]
+                else:
+                    s[pos:pos] = list(rng.choice(list("ACGT"), int(rng.integers(100, 600))))
+            s = [("ACGT"[int(rng.integers(0, 4))] if rng.random() < 0.01 else c) for c in s]
+            reads.append("".join(s))
+        if g == 0:
+            reads.insert(2, "".join(rng.choice(list("ACGT"), 8500)))       # unrelated read: no anchors, wide scores
+        groups.append(reads)
+    packed = pack_groups(groups)
+    flags = np.ones(len(groups), np.uint8)
+    want = oracle_consensus_batch(packed=packed, trace=True, n_threads=THREADS, flags=flags)
+    got = gpu_ctx.consensus_batch(packed=packed, trace=True, flags=flags)
+    assert_same(got, want, packed)
