@@ -269,6 +269,14 @@ extern "C" int mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups, const int64_t 
         const int w = ctx->params.wb + (int)(ctx->params.wf * (float)gi.maxlen);
         gi.wneed = 2 * w + 1 + (gi.maxlen - gi.minlen) + 2 * ctx->params.simd_pn_i16;
         gi.wneed = std::min(gi.wneed, gi.maxlen + 1 + 2 * ctx->params.simd_pn_i16);
+        if (group_flags && (group_flags[g] & MPOA_FLAG_SEED)) {
+            /* `abpoa -S`: the band belongs to a window between two anchors (>= MPOA_SEED_MIN_W apart, rarely
+             * more than a few of those), not to the whole read; a read that shares no anchor with its
+             * predecessor outgrows this and is re-run wider (ST_RETRY_WIDE) */
+            const int wl = std::min<int>(gi.maxlen, 4 * MPOA_SEED_MIN_W);
+            const int ww = ctx->params.wb + (int)(ctx->params.wf * (float)wl);
+            gi.wneed = std::min(gi.wneed, 2 * ww + 1 + 3 * ctx->params.simd_pn_i16);
+        }
         gi.cost = (double)gi.sumlen * (double)gi.wneed;
         /* the packed kernels keep scores relative to the diagonal, so they serve abPOA's int16 AND int32
          * lane widths; a group leaves them only when the kernel itself asks for it (ST_RETRY_32) */
@@ -301,7 +309,6 @@ extern "C" int mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups, const int64_t 
         const int nt = (int)std::max(1u, std::thread::hardware_concurrency());
         seed_batch(n_groups, ctx->h_gro.data(), ctx->h_rbo.data(), bases, ctx->h_flags.data(), MPOA_SEED_K, MPOA_SEED_W,
                    MPOA_SEED_MIN_W, nt, anc_off, anc);
-        if (getenv("MPOA_SEED_NOANCHOR")) { std::fill(anc_off.begin(), anc_off.end(), 0); anc.clear(); }   // debugging aid
         CK(ctx->b_anc_off.ensure(anc_off.size() * sizeof(int32_t)));
         CK(ctx->b_anc.ensure(std::max<size_t>(anc.size(), 2) * sizeof(int32_t)));
         ctx->d_anc_off = (int32_t *)ctx->b_anc_off.p; ctx->d_anc = (int2 *)ctx->b_anc.p;
