@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MPOA_ABI_VERSION 2
+#define MPOA_ABI_VERSION 3
 
 /* error codes (negative return values) */
 #define MPOA_OK          0
@@ -183,6 +183,40 @@ int  mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups,
 int  mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats);
 int  mpoa_batch_fetch(mpoa_ctx *ctx, int64_t *cons_off, uint8_t *cons_buf, int64_t cons_cap,
                       int32_t *group_status, mpoa_trace *trace);
+
+/*
+ * mpoa_batch_upload() for a SUBSET of the caller's groups: sel[n_sel] are ascending indices into the
+ * n_groups groups described by the offset arrays; the context then holds a batch of n_sel groups,
+ * numbered in sel order (group_flags is still indexed by the caller's group numbers).  The bases of
+ * the selected groups are gathered straight from the caller's buffer into the pinned staging buffers
+ * of the copy -- no intermediate host copy of the shard.
+ */
+int  mpoa_batch_upload_subset(mpoa_ctx *ctx, int64_t n_groups,
+                              const int64_t *group_read_off, const int64_t *read_base_off,
+                              const uint8_t *bases, const uint8_t *group_flags,
+                              int64_t n_sel, const int64_t *sel);
+
+/*
+ * ONE batch over several GPUs of one box.  The reference spreads isoform groups over a fork pool
+ * (defineIsoforms.py:130-153) and they never exchange data (:88-90), so the batch is cut into
+ * cost-balanced shards and every shard runs on its own GPU: no collective, no peer traffic.
+ *
+ * mpoa_shard_plan: owner[g] in [0, n_shards) by longest-processing-time greedy over the estimated DP
+ * cost of a group (sum of read lengths x expected band width); deterministic.  p NULL = defaults.
+ *
+ * mpoa_consensus_batch_multi: mpoa_consensus_batch() over ctxs[0..n_ctx) (distinct contexts, normally
+ * one per GPU).  One host thread per context uploads its shard (mpoa_batch_upload_subset), runs it
+ * and fetches it; results come back in INPUT order.  stats: n_ctx entries or NULL (per device);
+ * owner: n_groups entries or NULL (the plan that was used).  On error the message is in
+ * mpoa_last_error(ctxs[0]).
+ */
+int  mpoa_shard_plan(int64_t n_groups, const int64_t *group_read_off, const int64_t *read_base_off,
+                     const uint8_t *group_flags, const mpoa_params *p, int32_t n_shards, int32_t *owner);
+int  mpoa_consensus_batch_multi(mpoa_ctx *const *ctxs, int32_t n_ctx, int64_t n_groups,
+                                const int64_t *group_read_off, const int64_t *read_base_off,
+                                const uint8_t *bases, const uint8_t *group_flags,
+                                int64_t *cons_off, uint8_t *cons_buf, int64_t cons_cap,
+                                int32_t *group_status, mpoa_stats *stats, int32_t *owner);
 
 /*
  * Orientation of every read of a group against the group's FIRST read -- what the reference

@@ -8,10 +8,12 @@
  * of the reference (utils/SpliceDefineConsensus.py:917), one per group.
  */
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -24,8 +26,9 @@ namespace mpoa {
 cudaError_t launch_encode(const uint8_t *ascii, uint8_t *codes, int64_t n, cudaStream_t stream);
 cudaError_t launch_poa(int code, const KernelArgs &A, int n_blocks, int warps_per_block, cudaStream_t stream);
 int poa_max_blocks_per_sm(int code, int wcap, int warps_per_block, bool seeded);
-void seed_batch(int64_t n_groups, const int64_t *gro, const int64_t *rbo, const uint8_t *bases, const uint8_t *flags,
-                int k, int w, int min_gap, int n_threads, std::vector<int32_t> &anc_off, std::vector<int32_t> &anc);
+void seed_batch(int64_t n_groups, const int64_t *gro, const int64_t *rbo, const uint8_t *bases, const int64_t *src_off,
+                const uint8_t *flags, int k, int w, int min_gap, int n_threads, std::vector<int32_t> &anc_off,
+                std::vector<int32_t> &anc);
 size_t poa_smem_bytes(int code, int wcap, int warps_per_block);
 bool variant_exists(int code);
 cudaError_t launch_int_peak(uint32_t *out, int blocks, int iters, cudaStream_t stream);
@@ -61,6 +64,66 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+/*
+ * Host -> device copy of the bases through pinned staging buffers, filled by a few host threads.
+ * The caller's buffer is ordinary (pageable) memory in every real integration (numpy arrays, Python
+ * bytes): the driver's own pageable path copies at about 10 GB/s (measured: 1.66 GB in 155 ms); a few
+ * threads that memcpy into pinned chunks and issue the chunks on their own streams reach 35-46 GB/s.  The same path
+ * gathers a SUBSET of the groups (segments of the caller's buffer) without an intermediate copy.
+ */
+struct Seg { const uint8_t *src; int64_t dst, len; };   // in destination order, dst = prefix sum of len
+
+struct Stager {
+    static constexpr int K = 8;          // most copy threads (MPOA_STAGE_THREADS, default 6)
+    static constexpr size_t CH = 8u << 20;
+    cudaStream_t st[K] = {};
+    uint8_t *pin[K][2] = {};
+    cudaEvent_t ev[K][2] = {};
+    bool ready = false;
+    cudaError_t init() {
+        if (ready) return cudaSuccess;
+        for (int w = 0; w < K; ++w) {
+            cudaError_t e = cudaStreamCreateWithFlags(&st[w], cudaStreamNonBlocking);
+            for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+                e = cudaHostAlloc((void **)&pin[w][b], CH, cudaHostAllocDefault);
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[w][b], cudaEventDisableTiming);
+            }
+            if (e != cudaSuccess) return e;
+        }
+        ready = true;
+        return cudaSuccess;
+    }
+    void release() {
+        for (int w = 0; w < K; ++w) {
+            for (int b = 0; b < 2; ++b) {
+                if (pin[w][b]) cudaFreeHost(pin[w][b]);
+                if (ev[w][b]) cudaEventDestroy(ev[w][b]);
+                pin[w][b] = nullptr; ev[w][b] = nullptr;
+            }
+            if (st[w]) cudaStreamDestroy(st[w]);
+            st[w] = nullptr;
+        }
+        ready = false;
+    }
+};
+
+/* expected band width of a group in cells: widest band row seen on calibration sets (oracle, every
+ * named config) is never more than 2w+1 + length spread + two SIMD vectors of rounding */
+static int band_need(const mpoa_params &p, int maxlen, int minlen, bool seeded) {
+    const int w = p.wb + (int)(p.wf * (float)maxlen);
+    int need = 2 * w + 1 + (maxlen - minlen) + 2 * p.simd_pn_i16;
+    need = std::min(need, maxlen + 1 + 2 * p.simd_pn_i16);
+    if (seeded) {
+        /* `abpoa -S`: the band belongs to a window between two anchors (>= MPOA_SEED_MIN_W apart, rarely
+         * more than a few of those), not to the whole read; a read that shares no anchor with its
+         * predecessor outgrows this and is re-run wider (ST_RETRY_WIDE) */
+        const int wl = std::min<int>(maxlen, 4 * MPOA_SEED_MIN_W);
+        const int ww = p.wb + (int)(p.wf * (float)wl);
+        need = std::min(need, 2 * ww + 1 + 3 * p.simd_pn_i16);
+    }
+    return need;
+}
+
 struct mpoa_ctx {
     int dev = 0;
     int n_sm = 0;
@@ -72,6 +135,8 @@ struct mpoa_ctx {
     /* uploaded batch */
     int64_t n_groups = 0, n_reads = 0, n_bases = 0;
     std::vector<int64_t> h_gro, h_rbo;
+    std::vector<int64_t> h_src;                // subset upload: start of every read in the caller's buffer
+    Stager stager;
     std::vector<uint8_t> h_flags;              // MPOA_FLAG_* per group (empty: none set)
     std::vector<GroupInfo> ginfo;
     uint8_t *d_codes = nullptr;
@@ -176,6 +241,7 @@ extern "C" void mpoa_destroy(mpoa_ctx *ctx) {
     if (ctx->join2_ev) cudaEventDestroy(ctx->join2_ev);
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->side2) cudaStreamDestroy(ctx->side2);
+    ctx->stager.release();
     delete ctx;
 }
 
@@ -218,65 +284,150 @@ extern "C" int mpoa_measure_int_peak(mpoa_ctx *ctx, double *warp_instr_per_sec) 
     return MPOA_OK;
 }
 
-extern "C" int mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups, const int64_t *group_read_off,
-                                 const int64_t *read_base_off, const uint8_t *bases, const uint8_t *group_flags) {
-    if (!ctx || n_groups < 0) return MPOA_EINVAL;
-    if (n_groups > 0 && (!group_read_off || !read_base_off)) { ctx->err = "null offsets"; return MPOA_EINVAL; }
+/* one worker: bytes [lo, hi) of the destination */
+static cudaError_t stage_range(Stager &sg, int w, int dev, uint8_t *d_dst, const std::vector<Seg> &segs, int64_t lo, int64_t hi) {
+    cudaError_t e = cudaSetDevice(dev);
+    if (e != cudaSuccess) return e;
+    size_t s = (size_t)(std::upper_bound(segs.begin(), segs.end(), lo, [](int64_t v, const Seg &x) { return v < x.dst; }) - segs.begin());
+    s = s > 0 ? s - 1 : 0;
+    int it = 0;
+    for (int64_t pos = lo; pos < hi; ++it) {
+        const int b = it & 1;
+        const int64_t n = std::min<int64_t>((int64_t)Stager::CH, hi - pos);
+        if (it >= 2 && (e = cudaEventSynchronize(sg.ev[w][b])) != cudaSuccess) return e;
+        int64_t done = 0;
+        while (done < n) {
+            while (s + 1 < segs.size() && segs[s + 1].dst <= pos + done) ++s;
+            const Seg &x = segs[s];
+            const int64_t in_seg = pos + done - x.dst;
+            const int64_t take = std::min<int64_t>(n - done, x.len - in_seg);
+            std::memcpy(sg.pin[w][b] + done, x.src + in_seg, (size_t)take);
+            done += take;
+        }
+        if ((e = cudaMemcpyAsync(d_dst + pos, sg.pin[w][b], (size_t)n, cudaMemcpyHostToDevice, sg.st[w])) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(sg.ev[w][b], sg.st[w])) != cudaSuccess) return e;
+        pos += n;
+    }
+    return cudaStreamSynchronize(sg.st[w]);
+}
+
+static bool is_pageable(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+/*
+ * Upload of the whole batch (sel == nullptr) or of the groups sel[0..n_sel) (ascending indices into
+ * the caller's arrays): the context then holds a batch of n_sel groups numbered in sel order.
+ */
+static int upload_impl(mpoa_ctx *ctx, int64_t n_all, const int64_t *group_read_off, const int64_t *read_base_off,
+                       const uint8_t *bases, const uint8_t *group_flags, int64_t n_sel, const int64_t *sel) {
+    if (!ctx || n_all < 0 || (sel && n_sel < 0)) return MPOA_EINVAL;
+    if (n_all > 0 && (!group_read_off || !read_base_off)) { ctx->err = "null offsets"; return MPOA_EINVAL; }
     CK(cudaSetDevice(ctx->dev));
     free_batch(ctx);
+    const int64_t n_groups = sel ? n_sel : n_all;
     if (n_groups == 0) return MPOA_OK;
-    if (n_groups > INT_MAX / 2) { ctx->err = "too many groups"; return MPOA_EINVAL; }
-    const int64_t n_reads = group_read_off[n_groups];
-    if (group_read_off[0] != 0 || n_reads < 0) { ctx->err = "group_read_off must start at 0"; return MPOA_EINVAL; }
-    const int64_t n_bases = n_reads > 0 ? read_base_off[n_reads] : 0;
-    if (n_reads > 0 && (read_base_off[0] != 0 || n_bases < 0 || (n_bases > 0 && !bases))) {
+    if (n_all > INT_MAX / 2) { ctx->err = "too many groups"; return MPOA_EINVAL; }
+    const int64_t n_reads_all = group_read_off[n_all];
+    if (group_read_off[0] != 0 || n_reads_all < 0) { ctx->err = "group_read_off must start at 0"; return MPOA_EINVAL; }
+    const int64_t n_bases_all = n_reads_all > 0 ? read_base_off[n_reads_all] : 0;
+    if (n_reads_all > 0 && (read_base_off[0] != 0 || n_bases_all < 0 || (n_bases_all > 0 && !bases))) {
         ctx->err = "bad read_base_off / bases";
         return MPOA_EINVAL;
     }
-    /* the one big copy (the bases, from the caller's buffer) is issued first: the host-side pass over
-     * the offsets below runs while it is in flight */
-    cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;
-    CK(cudaEventRecord(e0, ctx->stream));
+    const auto t_start = std::chrono::steady_clock::now();
+
+    /* the batch's own offset arrays (a subset is renumbered), validated as they are built */
+    ctx->h_gro.assign(n_groups + 1, 0);
+    ctx->h_src.clear();
+    std::vector<Seg> segs;
+    if (!sel) {
+        ctx->h_gro.assign(group_read_off, group_read_off + n_groups + 1);
+        ctx->h_rbo.assign(read_base_off, read_base_off + n_reads_all + 1);
+        for (int64_t g = 0; g < n_groups; ++g)
+            if (ctx->h_gro[g + 1] < ctx->h_gro[g] || ctx->h_gro[g + 1] > n_reads_all) { ctx->err = "group_read_off not monotone"; return MPOA_EINVAL; }
+        for (int64_t r = 0; r < n_reads_all; ++r) {
+            const int64_t len = ctx->h_rbo[r + 1] - ctx->h_rbo[r];
+            if (len < 0 || len > (1 << 26)) { ctx->err = "bad read length"; return MPOA_EINVAL; }
+        }
+        if (group_flags) ctx->h_flags.assign(group_flags, group_flags + n_groups); else ctx->h_flags.clear();
+        if (n_bases_all > 0) segs.push_back(Seg{bases, 0, n_bases_all});
+    } else {
+        ctx->h_rbo.assign(1, 0);
+        if (group_flags) ctx->h_flags.resize(n_groups); else ctx->h_flags.clear();
+        int64_t prev = -1;
+        for (int64_t k = 0; k < n_groups; ++k) {
+            const int64_t g = sel[k];
+            if (g <= prev || g >= n_all) { ctx->err = "subset indices must be ascending and in range"; return MPOA_EINVAL; }
+            prev = g;
+            const int64_t r0 = group_read_off[g], r1 = group_read_off[g + 1];
+            if (r0 < 0 || r1 < r0 || r1 > n_reads_all) { ctx->err = "group_read_off not monotone"; return MPOA_EINVAL; }
+            ctx->h_gro[k + 1] = ctx->h_gro[k] + (r1 - r0);
+            for (int64_t r = r0; r < r1; ++r) {
+                const int64_t len = read_base_off[r + 1] - read_base_off[r];
+                if (len < 0 || len > (1 << 26) || read_base_off[r + 1] > n_bases_all) { ctx->err = "bad read length"; return MPOA_EINVAL; }
+                ctx->h_src.push_back(read_base_off[r]);
+                ctx->h_rbo.push_back(ctx->h_rbo.back() + len);
+            }
+            if (group_flags) ctx->h_flags[k] = group_flags[g];
+            const int64_t b0 = read_base_off[r0], b1 = read_base_off[r1];
+            if (b1 > b0) {
+                if (!segs.empty() && segs.back().src + segs.back().len == bases + b0) segs.back().len += b1 - b0;
+                else segs.push_back(Seg{bases + b0, segs.empty() ? 0 : segs.back().dst + segs.back().len, b1 - b0});
+            }
+        }
+    }
+    const int64_t n_reads = ctx->h_gro[n_groups];
+    const int64_t n_bases = ctx->h_rbo[n_reads];
+
+    /* the one big copy (the bases) starts first: the host-side passes below run while it is in flight */
     const size_t nb = (size_t)std::max<int64_t>(n_bases, 16);
     CK(ctx->b_ascii.ensure(nb)); CK(ctx->b_codes.ensure(nb));
     uint8_t *d_ascii = (uint8_t *)ctx->b_ascii.p;
-    if (n_bases > 0) CK(cudaMemcpyAsync(d_ascii, bases, n_bases, cudaMemcpyHostToDevice, ctx->stream));
-    auto fail = [&](const char *msg) {      // the caller's buffer must not be read after we return
+    std::vector<std::thread> copiers;
+    cudaError_t copy_err[Stager::K] = {};
+    const bool staged = n_bases > 0 && (sel != nullptr || (n_bases >= (int64_t)(4u << 20) && is_pageable(bases)));
+    if (staged) {
+        CK(ctx->stager.init());
+        CK(cudaStreamSynchronize(ctx->stream));          // earlier work on this buffer (it held the last batch's consensi)
+        int want = 6;
+        if (const char *e = getenv("MPOA_STAGE_THREADS")) want = std::max(1, std::min((int)Stager::K, atoi(e)));
+        const int nw = (int)std::min<int64_t>(want, (n_bases + (int64_t)Stager::CH - 1) / (int64_t)Stager::CH);
+        for (int w = 0; w < nw; ++w) {
+            const int64_t lo = n_bases * w / nw / 512 * 512, hi = w + 1 == nw ? n_bases : n_bases * (w + 1) / nw / 512 * 512;
+            copiers.emplace_back([&, w, lo, hi]() { copy_err[w] = stage_range(ctx->stager, w, ctx->dev, d_ascii, segs, lo, hi); });
+        }
+    } else if (n_bases > 0) CK(cudaMemcpyAsync(d_ascii, bases, n_bases, cudaMemcpyHostToDevice, ctx->stream));
+    auto join_copiers = [&]() { for (auto &t : copiers) t.join(); copiers.clear(); };
+    auto fail = [&](int code, const std::string &msg) {   // the caller's buffer must not be read after we return
+        join_copiers();
         cudaStreamSynchronize(ctx->stream);
         ctx->err = msg;
-        return (int)MPOA_EINVAL;
+        return code;
     };
-    if (group_flags) ctx->h_flags.assign(group_flags, group_flags + n_groups); else ctx->h_flags.clear();
-    ctx->h_gro.assign(group_read_off, group_read_off + n_groups + 1);
-    ctx->h_rbo.assign(read_base_off, read_base_off + n_reads + 1);
+#define CKU(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(_e == cudaErrorMemoryAllocation ? MPOA_ENOMEM : MPOA_ECUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
     ctx->ginfo.resize(n_groups);
     for (int64_t g = 0; g < n_groups; ++g) {
         GroupInfo &gi = ctx->ginfo[g];
         const int64_t r0 = ctx->h_gro[g], r1 = ctx->h_gro[g + 1];
-        if (r1 < r0 || r1 > n_reads) return fail("group_read_off not monotone");
         gi.n_reads = (int32_t)(r1 - r0);
         gi.maxlen = 0; gi.minlen = INT_MAX; gi.sumlen = 0;
         for (int64_t r = r0; r < r1; ++r) {
             const int64_t len = ctx->h_rbo[r + 1] - ctx->h_rbo[r];
-            if (len < 0 || len > (1 << 26)) return fail("bad read length");
             gi.maxlen = std::max<int32_t>(gi.maxlen, (int32_t)len);
             gi.minlen = std::min<int32_t>(gi.minlen, (int32_t)len);
             gi.sumlen += len;
         }
         if (gi.n_reads == 0) gi.minlen = 0;
-        /* widest band row seen on calibration sets (oracle, every named config): never more than
-         * 2w+1 + length spread + two SIMD vectors of rounding */
-        const int w = ctx->params.wb + (int)(ctx->params.wf * (float)gi.maxlen);
-        gi.wneed = 2 * w + 1 + (gi.maxlen - gi.minlen) + 2 * ctx->params.simd_pn_i16;
-        gi.wneed = std::min(gi.wneed, gi.maxlen + 1 + 2 * ctx->params.simd_pn_i16);
-        if (group_flags && (group_flags[g] & MPOA_FLAG_SEED)) {
-            /* `abpoa -S`: the band belongs to a window between two anchors (>= MPOA_SEED_MIN_W apart, rarely
-             * more than a few of those), not to the whole read; a read that shares no anchor with its
-             * predecessor outgrows this and is re-run wider (ST_RETRY_WIDE) */
-            const int wl = std::min<int>(gi.maxlen, 4 * MPOA_SEED_MIN_W);
-            const int ww = ctx->params.wb + (int)(ctx->params.wf * (float)wl);
-            gi.wneed = std::min(gi.wneed, 2 * ww + 1 + 3 * ctx->params.simd_pn_i16);
-        }
+        gi.wneed = band_need(ctx->params, gi.maxlen, gi.minlen, !ctx->h_flags.empty() && (ctx->h_flags[g] & MPOA_FLAG_SEED));
         gi.cost = (double)gi.sumlen * (double)gi.wneed;
         /* the packed kernels keep scores relative to the diagonal, so they serve abPOA's int16 AND int32
          * lane widths; a group leaves them only when the kernel itself asks for it (ST_RETRY_32) */
@@ -285,53 +436,65 @@ extern "C" int mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups, const int64_t 
     }
     ctx->n_groups = n_groups; ctx->n_reads = n_reads; ctx->n_bases = n_bases;
 
-    CK(ctx->b_rbo.ensure((n_reads + 1) * sizeof(int64_t))); CK(ctx->b_gro.ensure((n_groups + 1) * sizeof(int64_t)));
-    CK(ctx->b_region.ensure((n_groups + 1) * sizeof(int64_t)));
-    CK(ctx->b_len.ensure(n_groups * sizeof(int32_t))); CK(ctx->b_status.ensure(n_groups * sizeof(int32_t)));
-    CK(ctx->b_queue.ensure(n_groups * sizeof(int32_t)));
+    CKU(ctx->b_rbo.ensure((n_reads + 1) * sizeof(int64_t))); CKU(ctx->b_gro.ensure((n_groups + 1) * sizeof(int64_t)));
+    CKU(ctx->b_region.ensure((n_groups + 1) * sizeof(int64_t)));
+    CKU(ctx->b_len.ensure(n_groups * sizeof(int32_t))); CKU(ctx->b_status.ensure(n_groups * sizeof(int32_t)));
+    CKU(ctx->b_queue.ensure(n_groups * sizeof(int32_t)));
     ctx->d_codes = (uint8_t *)ctx->b_codes.p;
     ctx->d_rbo = (int64_t *)ctx->b_rbo.p; ctx->d_gro = (int64_t *)ctx->b_gro.p; ctx->d_region_off = (int64_t *)ctx->b_region.p;
     /* the ASCII input is dead once it is encoded: its buffer becomes the consensus regions */
     ctx->d_cons = d_ascii;
     ctx->d_cons_len = (int32_t *)ctx->b_len.p; ctx->d_status = (int32_t *)ctx->b_status.p; ctx->d_queue = (int32_t *)ctx->b_queue.p;
-    CK(cudaMemcpyAsync(ctx->d_rbo, ctx->h_rbo.data(), (n_reads + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_gro, ctx->h_gro.data(), (n_groups + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CKU(cudaMemcpyAsync(ctx->d_rbo, ctx->h_rbo.data(), (n_reads + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CKU(cudaMemcpyAsync(ctx->d_gro, ctx->h_gro.data(), (n_groups + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     /* consensus region of a group = the byte range of its reads: a consensus is a path of the
      * graph and can never hold more nodes than the group has bases */
     std::vector<int64_t> region(n_groups + 1);
     for (int64_t g = 0; g <= n_groups; ++g) region[g] = ctx->h_rbo[ctx->h_gro[g]];
-    CK(cudaMemcpyAsync(ctx->d_region_off, region.data(), (n_groups + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CKU(cudaMemcpyAsync(ctx->d_region_off, region.data(), (n_groups + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     /* `abpoa -S` groups: their anchors are computed here, on the host threads, while the copies are in flight */
     ctx->n_seed_groups = 0;
     for (uint8_t f : ctx->h_flags) ctx->n_seed_groups += (f & MPOA_FLAG_SEED) ? 1 : 0;
+    std::vector<int32_t> anc_off, anc;
     if (ctx->n_seed_groups > 0) {
-        std::vector<int32_t> anc_off, anc;
         const int nt = (int)std::max(1u, std::thread::hardware_concurrency());
-        seed_batch(n_groups, ctx->h_gro.data(), ctx->h_rbo.data(), bases, ctx->h_flags.data(), MPOA_SEED_K, MPOA_SEED_W,
-                   MPOA_SEED_MIN_W, nt, anc_off, anc);
-        CK(ctx->b_anc_off.ensure(anc_off.size() * sizeof(int32_t)));
-        CK(ctx->b_anc.ensure(std::max<size_t>(anc.size(), 2) * sizeof(int32_t)));
+        seed_batch(n_groups, ctx->h_gro.data(), ctx->h_rbo.data(), bases, ctx->h_src.empty() ? nullptr : ctx->h_src.data(),
+                   ctx->h_flags.data(), MPOA_SEED_K, MPOA_SEED_W, MPOA_SEED_MIN_W, nt, anc_off, anc);
+        CKU(ctx->b_anc_off.ensure(anc_off.size() * sizeof(int32_t)));
+        CKU(ctx->b_anc.ensure(std::max<size_t>(anc.size(), 2) * sizeof(int32_t)));
         ctx->d_anc_off = (int32_t *)ctx->b_anc_off.p; ctx->d_anc = (int2 *)ctx->b_anc.p;
-        CK(cudaMemcpyAsync(ctx->d_anc_off, anc_off.data(), anc_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-        if (!anc.empty()) CK(cudaMemcpyAsync(ctx->d_anc, anc.data(), anc.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));   // anc_off / anc are locals
+        CKU(cudaMemcpyAsync(ctx->d_anc_off, anc_off.data(), anc_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        if (!anc.empty()) CKU(cudaMemcpyAsync(ctx->d_anc, anc.data(), anc.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
-    CK(launch_encode(d_ascii, ctx->d_codes, n_bases, ctx->stream));
+    join_copiers();
+    for (int w = 0; w < Stager::K; ++w) CKU(copy_err[w]);
+    CKU(launch_encode(d_ascii, ctx->d_codes, n_bases, ctx->stream));
     if (ctx->want_trace) {
         const size_t nr = (size_t)std::max<int64_t>(n_reads, 1);
-        CK(ctx->b_tr_score.ensure(nr * sizeof(int32_t))); CK(ctx->b_tr_bits.ensure(nr * sizeof(int32_t)));
-        CK(ctx->b_tr_cells.ensure(nr * sizeof(long long)));
-        CK(ctx->b_tr_aln.ensure(nb * sizeof(int32_t))); CK(ctx->b_tr_node.ensure(nb * sizeof(int32_t)));
+        CKU(ctx->b_tr_score.ensure(nr * sizeof(int32_t))); CKU(ctx->b_tr_bits.ensure(nr * sizeof(int32_t)));
+        CKU(ctx->b_tr_cells.ensure(nr * sizeof(long long)));
+        CKU(ctx->b_tr_aln.ensure(nb * sizeof(int32_t))); CKU(ctx->b_tr_node.ensure(nb * sizeof(int32_t)));
         ctx->d_tr_score = (int32_t *)ctx->b_tr_score.p; ctx->d_tr_bits = (int32_t *)ctx->b_tr_bits.p;
         ctx->d_tr_cells = (long long *)ctx->b_tr_cells.p;
         ctx->d_tr_aln = (int32_t *)ctx->b_tr_aln.p; ctx->d_tr_node = (int32_t *)ctx->b_tr_node.p;
     }
-    CK(cudaEventRecord(e1, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    ctx->h2d_ms = ms;
+    CKU(cudaStreamSynchronize(ctx->stream));      // region / anc_off / anc are locals; the caller's buffer is free again
+#undef CKU
+    ctx->h2d_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
     return MPOA_OK;
+}
+
+extern "C" int mpoa_batch_upload(mpoa_ctx *ctx, int64_t n_groups, const int64_t *group_read_off,
+                                 const int64_t *read_base_off, const uint8_t *bases, const uint8_t *group_flags) {
+    return upload_impl(ctx, n_groups, group_read_off, read_base_off, bases, group_flags, 0, nullptr);
+}
+
+extern "C" int mpoa_batch_upload_subset(mpoa_ctx *ctx, int64_t n_groups, const int64_t *group_read_off,
+                                        const int64_t *read_base_off, const uint8_t *bases, const uint8_t *group_flags,
+                                        int64_t n_sel, const int64_t *sel) {
+    if (!sel && n_sel != 0) return MPOA_EINVAL;
+    static const int64_t none = 0;
+    return upload_impl(ctx, n_groups, group_read_off, read_base_off, bases, group_flags, n_sel, sel ? sel : &none);
 }
 
 /* capacities of one launch */
@@ -774,4 +937,114 @@ extern "C" int mpoa_consensus_batch(mpoa_ctx *ctx, int64_t n_groups, const int64
     ctx->want_trace = saved;
     if (stats) *stats = ctx->last;
     return rc;
+}
+
+/* ---- one batch over several GPUs of one box ---- */
+
+extern "C" int mpoa_shard_plan(int64_t n_groups, const int64_t *group_read_off, const int64_t *read_base_off,
+                               const uint8_t *group_flags, const mpoa_params *p, int32_t n_shards, int32_t *owner) {
+    if (n_groups < 0 || n_shards <= 0 || (n_groups > 0 && (!group_read_off || !read_base_off || !owner))) return MPOA_EINVAL;
+    mpoa_params dp;
+    if (p) dp = *p; else mpoa_default_params(&dp);
+    if (dp.simd_pn_i16 <= 0) dp.simd_pn_i16 = 16;
+    std::vector<double> cost(n_groups);
+    for (int64_t g = 0; g < n_groups; ++g) {
+        const int64_t r0 = group_read_off[g], r1 = group_read_off[g + 1];
+        if (r1 < r0) return MPOA_EINVAL;
+        int64_t sum = 0, mx = 0, mn = INT64_MAX;
+        for (int64_t r = r0; r < r1; ++r) {
+            const int64_t len = read_base_off[r + 1] - read_base_off[r];
+            sum += len; mx = std::max(mx, len); mn = std::min(mn, len);
+        }
+        if (r1 == r0) mn = 0;
+        /* reads 2..n are aligned; every row also pays a fixed cost (graph walk, traceback, merge) */
+        cost[g] = (double)sum * (double)(band_need(dp, (int)std::min<int64_t>(mx, 1 << 26), (int)std::min<int64_t>(mn, 1 << 26),
+                                                   group_flags && (group_flags[g] & MPOA_FLAG_SEED)) + 64);
+    }
+    /* longest-processing-time greedy: heaviest group first, each to the least loaded shard */
+    std::vector<int64_t> order(n_groups);
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return cost[a] != cost[b] ? cost[a] > cost[b] : a < b; });
+    std::vector<double> load(n_shards, 0.0);
+    for (int64_t g : order) {
+        int best = 0;
+        for (int s = 1; s < n_shards; ++s) if (load[s] < load[best]) best = s;
+        owner[g] = best;
+        load[best] += cost[g];
+    }
+    return MPOA_OK;
+}
+
+extern "C" int mpoa_consensus_batch_multi(mpoa_ctx *const *ctxs, int32_t n_ctx, int64_t n_groups,
+                                          const int64_t *group_read_off, const int64_t *read_base_off, const uint8_t *bases,
+                                          const uint8_t *group_flags, int64_t *cons_off, uint8_t *cons_buf, int64_t cons_cap,
+                                          int32_t *group_status, mpoa_stats *stats, int32_t *owner_out) {
+    if (!ctxs || n_ctx <= 0 || n_groups < 0 || !cons_off) return MPOA_EINVAL;
+    for (int k = 0; k < n_ctx; ++k) {
+        if (!ctxs[k]) return MPOA_EINVAL;
+        for (int j = 0; j < k; ++j) if (ctxs[j] == ctxs[k]) { ctxs[k]->err = "the same context twice"; return MPOA_EINVAL; }
+    }
+    cons_off[0] = 0;
+    if (stats) std::memset(stats, 0, sizeof(mpoa_stats) * (size_t)n_ctx);
+    if (n_groups == 0) return MPOA_OK;
+    std::vector<int32_t> owner(n_groups, 0);
+    if (n_ctx > 1) {
+        const int rc = mpoa_shard_plan(n_groups, group_read_off, read_base_off, group_flags, &ctxs[0]->params, n_ctx, owner.data());
+        if (rc != MPOA_OK) { ctxs[0]->err = "bad group offsets"; return rc; }
+    }
+    if (owner_out) std::copy(owner.begin(), owner.end(), owner_out);
+    struct Part {
+        std::vector<int64_t> sel, off;
+        std::vector<int32_t> status;
+        std::unique_ptr<uint8_t[]> buf;
+        int rc = MPOA_OK;
+    };
+    std::vector<Part> parts(n_ctx);
+    for (int64_t g = 0; g < n_groups; ++g) parts[owner[g]].sel.push_back(g);
+    auto run_part = [&](int k) {
+        Part &pt = parts[k];
+        mpoa_ctx *ctx = ctxs[k];
+        const int64_t n = (int64_t)pt.sel.size();
+        pt.off.assign(n + 1, 0);
+        pt.status.assign(n, MPOA_GROUP_EMPTY);
+        if (n == 0) { free_batch(ctx); return; }
+        pt.rc = upload_impl(ctx, n_groups, group_read_off, read_base_off, bases, group_flags, n, pt.sel.data());
+        if (pt.rc == MPOA_OK) pt.rc = mpoa_batch_run(ctx, nullptr);
+        if (pt.rc != MPOA_OK) return;
+        const int64_t cap = std::max<int64_t>(ctx->n_bases, 16);    // a consensus never outgrows its group's bases
+        pt.buf.reset(new uint8_t[cap]);
+        pt.rc = mpoa_batch_fetch(ctx, pt.off.data(), pt.buf.get(), cap, pt.status.data(), nullptr);
+        if (stats) stats[k] = ctx->last;
+    };
+    auto for_parts = [&](auto &&fn) {
+        if (n_ctx == 1) { fn(0); return; }
+        std::vector<std::thread> th;
+        for (int k = 0; k < n_ctx; ++k) th.emplace_back(fn, k);
+        for (auto &t : th) t.join();
+    };
+    for_parts(run_part);
+    for (int k = 0; k < n_ctx; ++k)
+        if (parts[k].rc != MPOA_OK) {
+            if (k != 0) ctxs[0]->err = "device " + std::to_string(ctxs[k]->dev) + ": " + ctxs[k]->err;
+            return parts[k].rc;
+        }
+    /* results back in input order */
+    for (int k = 0; k < n_ctx; ++k) {
+        const Part &pt = parts[k];
+        for (size_t i = 0; i < pt.sel.size(); ++i) cons_off[pt.sel[i] + 1] = pt.off[i + 1] - pt.off[i];
+    }
+    for (int64_t g = 0; g < n_groups; ++g) cons_off[g + 1] += cons_off[g];
+    if (cons_off[n_groups] > cons_cap || (cons_off[n_groups] > 0 && !cons_buf)) {
+        ctxs[0]->err = "cons_buf too small";
+        return MPOA_ENOSPC;
+    }
+    for_parts([&](int k) {
+        const Part &pt = parts[k];
+        for (size_t i = 0; i < pt.sel.size(); ++i) {
+            const int64_t g = pt.sel[i], n = pt.off[i + 1] - pt.off[i];
+            if (n > 0) std::memcpy(cons_buf + cons_off[g], pt.buf.get() + pt.off[i], (size_t)n);
+            if (group_status) group_status[g] = pt.status[i];
+        }
+    });
+    return MPOA_OK;
 }

@@ -125,10 +125,12 @@ void anchors_of(const std::vector<KmerAt> &prev_sorted, const std::vector<KmerAt
 /*
  * Anchors of every read of the flagged groups: anc_off[n_reads + 1] (prefix counts of anchors),
  * anc = (start in the previous read, start in this read) pairs.  Unflagged groups and first reads
- * have none.  n_threads host threads over groups.
+ * have none.  n_threads host threads over groups.  src_off (nullable): where read r starts in
+ * `bases` when the batch is a subset of the caller's arrays (default: rbo[r]).
  */
-void seed_batch(int64_t n_groups, const int64_t *gro, const int64_t *rbo, const uint8_t *bases, const uint8_t *flags,
-                int k, int w, int min_gap, int n_threads, std::vector<int32_t> &anc_off, std::vector<int32_t> &anc) {
+void seed_batch(int64_t n_groups, const int64_t *gro, const int64_t *rbo, const uint8_t *bases, const int64_t *src_off,
+                const uint8_t *flags, int k, int w, int min_gap, int n_threads, std::vector<int32_t> &anc_off,
+                std::vector<int32_t> &anc) {
     const int64_t n_reads = n_groups > 0 ? gro[n_groups] : 0;
     std::vector<std::vector<int32_t>> per_read((size_t)n_reads);
     std::atomic<int64_t> next(0);
@@ -145,7 +147,7 @@ void seed_batch(int64_t n_groups, const int64_t *gro, const int64_t *rbo, const 
             for (int64_t r = gro[g]; r < gro[g + 1]; ++r) {
                 const int len = (int)(rbo[r + 1] - rbo[r]);
                 if (len <= 0) continue;                 // an empty read is skipped by the aligner too
-                forward_minimizers(bases + rbo[r], len, w, k, *cur);
+                forward_minimizers(bases + (src_off ? src_off[r] : rbo[r]), len, w, k, *cur);
                 if (prev_r >= 0) {
                     /* *prev is already sorted by hash */
                     anchors_of(*prev, *cur, k, min_gap, hits, score, from, per_read[(size_t)r]);

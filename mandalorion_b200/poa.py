@@ -65,7 +65,8 @@ _lib = None
 # every symbol include/mandalorion_poa.h declares
 ABI_SYMBOLS = ("mpoa_abi_version", "mpoa_default_params", "mpoa_create", "mpoa_destroy", "mpoa_last_error",
                "mpoa_set_stream", "mpoa_set_trace", "mpoa_measure_int_peak", "mpoa_consensus_batch", "mpoa_batch_upload", "mpoa_batch_run",
-               "mpoa_batch_fetch", "mpoa_orient_batch")
+               "mpoa_batch_fetch", "mpoa_orient_batch", "mpoa_batch_upload_subset", "mpoa_shard_plan",
+               "mpoa_consensus_batch_multi")
 
 
 def _load():
@@ -90,6 +91,10 @@ def _load():
         lib.mpoa_batch_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         lib.mpoa_consensus_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6 + [C.c_int64] + [C.c_void_p] * 3
         lib.mpoa_orient_batch.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        lib.mpoa_batch_upload_subset.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]
+        lib.mpoa_shard_plan.argtypes = [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p]
+        lib.mpoa_consensus_batch_multi.argtypes = ([C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 6 + [C.c_int64]
+                                                   + [C.c_void_p] * 3)
         _lib = lib
     return _lib
 
@@ -131,14 +136,68 @@ def orient_batch(packed, n_threads=None):
     return cnt[:nr], strand[:nr]
 
 
+def _c_params(p):
+    p = p or PoaParams()
+    return _Params(p.match, p.mismatch, p.gap_open1, p.gap_ext1, p.gap_open2, p.gap_ext2, p.wb, p.wf,
+                   p.simd_pn_i16, p.simd_pn_i32, p.debug_small_caps)
+
+
+def shard_plan(packed, n_shards, flags=None, params=None):
+    """Owner (0..n_shards-1) of every group: longest-processing-time greedy over the estimated DP cost
+    (C ABI mpoa_shard_plan).  Host code: needs no GPU."""
+    lib = _load()
+    gro, rbo = [np.ascontiguousarray(a, dtype=np.int64) for a in packed[:2]]
+    if flags is not None:
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+    ng = len(gro) - 1
+    owner = np.zeros(max(ng, 1), dtype=np.int32)
+    cp = _c_params(params)
+    rc = lib.mpoa_shard_plan(ng, _ptr(gro), _ptr(rbo), _ptr(flags), C.byref(cp), int(n_shards), _ptr(owner))
+    if rc != 0:
+        raise PoaError(f"mpoa_shard_plan failed with {rc}")
+    return owner[:ng]
+
+
+def _split(raw, off):
+    off = off.tolist()
+    return [raw[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+
+
+def consensus_batch_multi(contexts, packed, flags=None):
+    """ONE batch over several PoaContexts (one per GPU) through the C ABI's
+    mpoa_consensus_batch_multi: native LPT sharding, one host thread per GPU, results in input
+    order.  Returns dict(cons=[bytes], status=int32[], stats=[dict per context], owner=int32[])."""
+    lib = _load()
+    gro, rbo, bases = [np.ascontiguousarray(a, dtype=t) for a, t in zip(packed, (np.int64, np.int64, np.uint8))]
+    if flags is not None:
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+    ng = len(gro) - 1
+    n = len(contexts)
+    handles = (C.c_void_p * n)(*[c._h for c in contexts])
+    cap = max(16, int(rbo[-1]) if len(rbo) else 0)
+    cons_buf = np.empty(cap, dtype=np.uint8)
+    cons_off = np.zeros(ng + 1, dtype=np.int64)
+    status = np.zeros(ng, dtype=np.int32)
+    owner = np.zeros(max(ng, 1), dtype=np.int32)
+    st = (_Stats * n)()
+    rc = lib.mpoa_consensus_batch_multi(handles, n, ng, _ptr(gro), _ptr(rbo), _ptr(bases), _ptr(flags), _ptr(cons_off),
+                                        _ptr(cons_buf), cap, _ptr(status), st, _ptr(owner))
+    if rc != 0:
+        msg = lib.mpoa_last_error(contexts[0]._h)
+        raise PoaError(f"mpoa_consensus_batch_multi failed with {rc}: {msg.decode() if msg else ''}")
+    stats = [PoaContext._stats_dict(x) for x in st]
+    for c, d in zip(contexts, stats):
+        c.last_stats = d
+    return dict(cons=_split(cons_buf[:cons_off[ng]].tobytes(), cons_off), status=status, cons_off=cons_off,
+                stats=stats, owner=owner[:ng])
+
+
 class PoaContext:
     """One context per (process, GPU); not thread-safe (include/mandalorion_poa.h)."""
 
     def __init__(self, device=0, params=None):
         lib = _load()
-        p = params or PoaParams()
-        cp = _Params(p.match, p.mismatch, p.gap_open1, p.gap_ext1, p.gap_open2, p.gap_ext2, p.wb, p.wf,
-                     p.simd_pn_i16, p.simd_pn_i32, p.debug_small_caps)
+        cp = _c_params(params)
         h = C.c_void_p()
         rc = lib.mpoa_create(C.byref(h), int(device), C.byref(cp))
         if rc != 0:
@@ -191,13 +250,21 @@ class PoaContext:
         return d
 
     # ---- three-stage interface (inputs stay resident in HBM between run() calls) ----
-    def upload(self, gro, rbo, bases, flags=None):
+    def upload(self, gro, rbo, bases, flags=None, subset=None):
+        """subset: ascending group indices -- only those groups are uploaded (numbered in that order)."""
         if flags is not None:
             flags = np.ascontiguousarray(flags, dtype=np.uint8)
         gro = np.ascontiguousarray(gro, dtype=np.int64)
         rbo = np.ascontiguousarray(rbo, dtype=np.int64)
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         ng = len(gro) - 1
+        if subset is not None:
+            sel = np.ascontiguousarray(subset, dtype=np.int64)
+            self._check(self._lib.mpoa_batch_upload_subset(self._h, ng, _ptr(gro), _ptr(rbo), _ptr(bases), _ptr(flags),
+                                                           len(sel), _ptr(sel)), "mpoa_batch_upload_subset")
+            reads = np.concatenate([np.arange(gro[g], gro[g + 1]) for g in sel]) if len(sel) else np.zeros(0, np.int64)
+            self._n = (len(sel), len(reads), int((rbo[reads + 1] - rbo[reads]).sum()) if len(reads) else 0)
+            return
         self._check(self._lib.mpoa_batch_upload(self._h, ng, _ptr(gro), _ptr(rbo), _ptr(bases), _ptr(flags)),
                     "mpoa_batch_upload")
         self._n = (ng, len(rbo) - 1, int(rbo[-1]) if len(rbo) else 0)
@@ -223,8 +290,7 @@ class PoaContext:
                           ("read_score", "read_bits", "read_band_cells", "base_aln", "base_node")])
         self._check(self._lib.mpoa_batch_fetch(self._h, _ptr(cons_off), _ptr(cons_buf), cap, _ptr(status),
                                                C.byref(tr) if tr is not None else None), "mpoa_batch_fetch")
-        raw = cons_buf[:cons_off[ng]].tobytes()
-        cons = [raw[cons_off[i]:cons_off[i + 1]] for i in range(ng)]
+        cons = _split(cons_buf[:cons_off[ng]].tobytes(), cons_off)
         return dict(cons=cons, status=status, cons_off=cons_off, trace=arrs)
 
     # ---- the one-call interface ----

@@ -4,8 +4,6 @@ Groups never exchange data (reference defineIsoforms.py:88-90 calls determine_co
 per isoform with no shared state), so there is no collective on the data path: every rank
 takes a cost-balanced subset, runs it on its own GPU and the host gathers the strings.
 """
-import threading
-
 import numpy as np
 
 
@@ -100,48 +98,32 @@ def consensus_batch_sharded(packed, devices=None, params=None, flags=None, conte
     (replaces the fork pool of reference defineIsoforms.py:130-153 for the consensus step).
 
     Groups are independent, so the batch is cut into cost-balanced shards (LPT over the estimated
-    DP cost), every shard runs on its own GPU from its own host thread (one PoaContext per GPU;
-    the C ABI releases the GIL) and the host puts the results back in input order.  No
-    collective, no peer traffic.
+    DP cost) and every shard runs on its own GPU.  All of it happens behind ONE C-ABI call
+    (mpoa_consensus_batch_multi): the plan, one host thread per GPU, the gather of a shard's bases
+    straight from the caller's buffer into the pinned staging buffers of its copy, and the results
+    back in input order.  No collective, no peer traffic.
 
     devices: CUDA ordinals (default: all visible).  contexts: optional {device: PoaContext} to reuse.
     Returns dict(cons=[bytes] in input order, status=int32[], stats=[per-device stats dict],
-    imbalance=max/mean of the per-device kernel time)."""
-    from .poa import PoaContext
-    gro, rbo, bases = [np.asarray(a) for a in packed]
+    imbalance=max/mean of the per-device kernel time, owner=int32[] shard of every group)."""
+    from .poa import PoaContext, consensus_batch_multi
     if devices is None:
         import torch
         devices = list(range(torch.cuda.device_count()))
     if not devices:
         raise RuntimeError("consensus_batch_sharded needs at least one CUDA device (there is no CPU path)")
-    n_groups = len(gro) - 1
-    owner = lpt_assign(group_costs(gro, rbo), len(devices)) if len(devices) > 1 else np.zeros(n_groups, np.int32)
-    results = [None] * len(devices)
-    errors = []
-
-    def work(k, dev):
-        try:
-            idx = np.nonzero(owner == k)[0]
-            g2, r2, b2 = (gro, rbo, bases) if len(devices) == 1 else take_shard_fast(gro, rbo, bases, idx)
-            f2 = None if flags is None else np.ascontiguousarray(np.asarray(flags, dtype=np.uint8)[idx])
-            ctx = contexts[dev] if contexts and dev in contexts else PoaContext(dev, params)
-            try:
-                out = ctx.consensus_batch(packed=(g2, r2, b2), flags=f2)
-            finally:
-                if not (contexts and dev in contexts):
-                    ctx.close()
-            results[k] = (idx, out["cons"], out["status"], out["stats"])
-        except Exception as e:       # re-raised in the caller's thread
-            errors.append(e)
-
-    threads = [threading.Thread(target=work, args=(k, dev)) for k, dev in enumerate(devices)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    if errors:
-        raise errors[0]
-    cons, status = merge_shards(n_groups, [(r[0], r[1], r[2]) for r in results])
-    kms = [r[3]["kernel_ms"] for r in results]
-    return dict(cons=cons, status=status, stats=[r[3] for r in results],
-                imbalance=max(kms) / max(1e-9, float(np.mean(kms))), owner=owner)
+    use, created = [], []
+    try:
+        for d in devices:                      # one context per entry: a device named twice gets two
+            c = contexts.get(d) if contexts else None
+            if c is None or any(c is u for u in use):
+                c = PoaContext(d, params)
+                created.append(c)
+            use.append(c)
+        out = consensus_batch_multi(use, packed, flags)
+    finally:
+        for c in created:
+            c.close()
+    kms = [s["kernel_ms"] for s in out["stats"]]
+    out["imbalance"] = max(kms) / max(1e-9, float(np.mean(kms)))
+    return out

@@ -25,7 +25,7 @@ def test_header_symbols_are_exported(built):
         assert hasattr(lib, s), f"{s} declared in the header but not exported"
     assert sorted(ABI_SYMBOLS) == syms
     lib.mpoa_abi_version.restype = ctypes.c_int
-    assert lib.mpoa_abi_version() == 2
+    assert lib.mpoa_abi_version() == 3
 
 
 def test_default_params_are_the_reference_command_line(built):

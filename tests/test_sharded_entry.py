@@ -1,45 +1,110 @@
-"""The product's multi-GPU entry point on CPU: shard.consensus_batch_sharded() with one test double
-per "device" (oracle-backed contexts, one host thread each).  Results must come back in input
-order and equal the single-context run; nothing is exchanged between shards."""
-import numpy as np
+"""The product's multi-GPU entry point.  On CPU: the native shard plan (mpoa_shard_plan: host code,
+no GPU).  On the GPU (-m gpu): mpoa_consensus_batch_multi and mpoa_batch_upload_subset against the
+oracle -- several contexts on one device stand in for several GPUs, the code path is the same."""
+import ctypes as C
 
-from helpers import OracleBackedContext, oracle_consensus_batch, pack_groups
+import numpy as np
+import pytest
+
+from helpers import oracle_consensus_batch, pack_groups
 from mandalorion_b200 import shard
+from mandalorion_b200.poa import shard_plan
 from mandalorion_b200.synth import GroupConfig, make_groups
 
 CFG = GroupConfig("shard2", 41, 0, 9, 60, 500, "loguniform", 0.03, (0.3, 0.35, 0.35))
 
 
-def test_sharded_batch_equals_the_single_context_run():
-    groups = make_groups(CFG)
+def test_native_plan_is_balanced_deterministic_and_complete(built):
+    packed = pack_groups(make_groups(CFG))
+    ng = len(packed[0]) - 1
+    cost = shard.group_costs(packed[0], packed[1])
+    for n in (1, 2, 5):
+        owner = shard_plan(packed, n)
+        assert len(owner) == ng and owner.min() >= 0 and owner.max() < n
+        assert owner.tolist() == shard_plan(packed, n).tolist()
+        if n > 1:
+            load = np.bincount(owner, weights=cost, minlength=n)
+            assert load.max() / load.mean() < 1.25
+    assert shard_plan(pack_groups([]), 3).tolist() == []
+    # a seeded group is cheaper than the same group unseeded (windowed band), never free
+    long_groups = pack_groups([[b"ACGT" * 3000] * 4, [b"ACGT" * 3000] * 4, [b"ACGT" * 3000] * 4])
+    assert shard_plan(long_groups, 2, flags=np.array([1, 1, 0], np.uint8)).tolist() == [1, 1, 0]
+    assert shard_plan(long_groups, 2).tolist() == [0, 1, 0]
+
+
+@pytest.mark.gpu
+def test_multi_context_batch_equals_the_oracle(gpu_ctx):
+    from mandalorion_b200 import PoaContext
+    from mandalorion_b200.poa import consensus_batch_multi
+    groups = make_groups(CFG) + [[], [b"ACGTTGCA" * 30]]
     packed = pack_groups(groups)
     want = oracle_consensus_batch(packed=packed)
-    for n_dev in (1, 2, 5):
-        ctxs = {d: OracleBackedContext() for d in range(n_dev)}
-        out = shard.consensus_batch_sharded(packed, devices=list(range(n_dev)), contexts=ctxs)
-        assert out["cons"] == want["cons"] and out["status"].tolist() == want["status"].tolist()
-        assert all(c.calls == 1 for c in ctxs.values())                      # one batch per device
-        assert sum(s["band_cells"] for s in out["stats"]) == want["stats"]["band_cells"]
-        if n_dev > 1:
-            cost = shard.group_costs(packed[0], packed[1])
-            load = np.bincount(out["owner"], weights=cost, minlength=n_dev)
-            assert load.max() / load.mean() < 1.25                            # cost-balanced shards
+    extra = [PoaContext(0) for _ in range(4)]
+    try:
+        for n in (1, 2, 5):
+            out = consensus_batch_multi(([gpu_ctx] + extra)[:n], packed)
+            assert out["cons"] == want["cons"] and out["status"].tolist() == want["status"].tolist()
+            assert sum(s["band_cells"] for s in out["stats"]) == want["stats"]["band_cells"]
+            assert sum(s["n_groups"] for s in out["stats"]) == len(groups)
+            assert out["owner"].tolist() == shard_plan(packed, n).tolist()
+        # the same context twice is refused
+        from mandalorion_b200 import PoaError
+        with pytest.raises(PoaError):
+            consensus_batch_multi([gpu_ctx, gpu_ctx], packed)
+        # more contexts than groups: empty shards are fine
+        tiny = pack_groups(groups[:2])
+        out = consensus_batch_multi([gpu_ctx] + extra, tiny)
+        assert out["cons"] == oracle_consensus_batch(packed=tiny)["cons"]
+    finally:
+        for c in extra:
+            c.close()
 
 
-def test_flags_travel_with_their_groups():
-    groups = make_groups(CFG)[:12]
+@pytest.mark.gpu
+def test_flags_travel_with_their_groups(gpu_ctx):
+    from mandalorion_b200 import PoaContext
+    from mandalorion_b200.poa import consensus_batch_multi
+    cfg = GroupConfig("shard_seed", 10, 3, 5, 1300, 1800, "uniform", 0.02, (0.3, 0.35, 0.35))
+    packed = pack_groups(make_groups(cfg))
+    flags = (np.arange(10) % 2).astype(np.uint8)
+    want = oracle_consensus_batch(packed=packed, flags=flags)
+    other = PoaContext(0)
+    try:
+        out = consensus_batch_multi([gpu_ctx, other], packed, flags=flags)
+    finally:
+        other.close()
+    assert out["cons"] == want["cons"]
+    assert sum(s["n_seed_groups"] for s in out["stats"]) == 5
+    assert sum(s["band_cells"] for s in out["stats"]) == want["stats"]["band_cells"]
+
+
+@pytest.mark.gpu
+def test_subset_upload_runs_only_the_selected_groups(gpu_ctx):
+    groups = make_groups(CFG)
     packed = pack_groups(groups)
-    flags = np.arange(12, dtype=np.uint8) % 2
-    seen = {}
+    flags = np.zeros(len(groups), np.uint8)
+    for sel in ([0], [3, 4, 5, 17, 40], list(range(len(groups))), []):
+        gpu_ctx.upload(*packed, flags=flags, subset=sel)
+        st = gpu_ctx.run()
+        out = gpu_ctx.fetch()
+        want = oracle_consensus_batch(packed=pack_groups([groups[g] for g in sel]))
+        assert out["cons"] == want["cons"] and st["band_cells"] == want["stats"]["band_cells"]
+    from mandalorion_b200 import PoaError
+    for bad in ([5, 3], [1, 1], [len(groups)], [-1]):
+        with pytest.raises(PoaError):
+            gpu_ctx.upload(*packed, subset=bad)
 
-    class Spy(OracleBackedContext):
-        def consensus_batch(self, groups=None, packed=None, trace=False, flags=None):
-            seen[id(self)] = (len(packed[0]) - 1, None if flags is None else flags.tolist())
-            return super().consensus_batch(packed=packed)
 
-    ctxs = {0: Spy(), 1: Spy()}
-    out = shard.consensus_batch_sharded(packed, devices=[0, 1], contexts=ctxs, flags=flags)
-    for k, c in ctxs.items():
-        n, f = seen[id(c)]
-        idx = np.nonzero(out["owner"] == k)[0]
-        assert n == len(idx) and f == flags[idx].tolist()
+@pytest.mark.gpu
+def test_multi_reports_a_too_small_result_buffer(gpu_ctx):
+    from mandalorion_b200.poa import _load
+    lib = _load()
+    gro, rbo, bases = pack_groups(make_groups(CFG)[:8])
+    ng = len(gro) - 1
+    off = np.zeros(ng + 1, np.int64)
+    buf = np.zeros(4, np.uint8)
+    status = np.zeros(ng, np.int32)
+    handles = (C.c_void_p * 1)(gpu_ctx._h)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    rc = lib.mpoa_consensus_batch_multi(handles, 1, ng, p(gro), p(rbo), p(bases), None, p(off), p(buf), 4, p(status), None, None)
+    assert rc == -4 and off[ng] == sum(len(c) for c in oracle_consensus_batch(packed=(gro, rbo, bases))["cons"])
