@@ -20,13 +20,21 @@ runs the batch through the CUDA library; both calls release the GIL, so parsing,
 the GPU overlap.  Results are identical to consensus.finish_prepared() -- batching never changes
 a group's consensus -- and come back in insertion order.
 
+define_isoforms() is the whole D step without the reference's Python on the path: locus files ->
+locus.locus_groups (the group producer) -> prepare_group -> streamed GPU batches ->
+Isoform_Consensi.fasta / reads2isoforms.txt, byte-identical to `python3 defineIsoforms.py ...`.
+
 iter_psl() reads the 24-column lines of tmp_SS/*.psl (emtrey.py:146-148; the columns module D uses
 are listed in SURVEY.md Appendix B.2) for producers that do not go through the reference's parser.
 """
+import os
 import queue
 import threading
 
-from .consensus import ConsensusBatcher, orient_pending
+import numpy as np
+
+from .consensus import ConsensusBatcher, orient_pending, prepare_group, write_isoform_files
+from .locus import locus_groups
 
 PSL_COLUMNS = dict(strand=8, name=9, length=10, qstart=11, qend=12, chrom=13, tstart=15, tend=16,
                    block_sizes=18, block_starts=20, accuracy=21, cs=22, sequence=23)
@@ -106,3 +114,44 @@ class StreamingConsensus:
     @property
     def stats(self):
         return self._batcher.stats
+
+
+def locus_roots(tmp_ss):
+    """Locus files of a tmp_SS directory in the reference's processing order (get_parsed_files,
+    utils/SpliceDefineConsensus.py:96-105; sorted by chromosome name, then start: defineIsoforms.py:126)."""
+    roots = {f.split(".psl")[0] for f in os.listdir(tmp_ss) if ".psl" in f}
+    return sorted(roots, key=lambda x: (x.split("~")[0], int(x.split("~")[1])))
+
+
+def define_isoforms(out_path, ctx=None, device=0, left_bounds=None, right_bounds=None, splice_site_width=1,
+                    minimum_read_count=2, junctions=("gtag", "gcag", "atac", "ctac", "ctgc", "gtat"), cutoff=0.1,
+                    upstream_buffer=10, downstream_buffer=50, batch_bases=256 << 20, orient_threads=None):
+    """Module D (`defineIsoforms.py -p out_path ...`, reference defineIsoforms.py:93-168) on one GPU:
+    reads out_path/tmp_SS/*.psl, writes out_path/Isoform_Consensi.fasta and reads2isoforms.txt.
+
+    left_bounds / right_bounds: annotated splice sites {chrom: {'5': [...], '3': [...]}} as the reference's
+    parse_genome() returns them (None: read-derived sites only, `-g None`).  The other arguments are the
+    command-line flags Mando.py passes (:382-398), same defaults.
+
+    Random numbers: the reference forks one worker per locus, so every locus starts from the PARENT's
+    NumPy RNG state; the same is done here (state saved at entry, restored before every locus), which makes
+    the output identical to a reference run started from the same state.  Returns the number of isoforms."""
+    tmp_ss = os.path.join(out_path, "tmp_SS")
+    roots = locus_roots(tmp_ss)
+    junctions = list(junctions)
+    entry_state = np.random.get_state()
+    sc = StreamingConsensus(ctx, device=device, batch_bases=batch_bases, orient_threads=orient_threads)
+    for root in roots:
+        chrom, start, end = root.split("~")
+        start, end = int(start), int(end)
+        inside = {}
+        for side, table in (("l", left_bounds), ("r", right_bounds)):
+            per = (table or {}).get(chrom, {"5": [], "3": []})
+            inside[side] = {k: [p for p in per[k] if start < p < end] for k in ("5", "3")}
+        np.random.set_state(entry_state)
+        groups = locus_groups(os.path.join(tmp_ss, root + ".psl"), chrom, inside["l"], inside["r"], splice_site_width,
+                              minimum_read_count, junctions, cutoff, upstream_buffer, downstream_buffer)
+        sc.add_locus(root, {isoform: prepare_group(reads) for isoform, reads in groups.items()})
+    results = sc.finish()
+    define_isoforms.last_stats = sc.stats
+    return write_isoform_files(roots, results, out_path)

@@ -104,3 +104,32 @@ def test_dstep_files_match_the_unmodified_reference(tmp_path):
     else:
         assert json.load(open(os.path.join(GOLD, "prepared.json"))) == frozen
         assert open(os.path.join(GOLD, "Isoform_Consensi.fasta"), "rb").read() == want_fa
+
+
+GOLD_SPLICED = os.path.join(HERE, "golden", "dstep_spliced")
+
+
+def test_whole_dstep_without_reference_code_on_the_path(tmp_path):
+    """define_isoforms(): locus files -> locus.locus_groups -> prepare_group -> batched consensus -> writer,
+    against `python3 defineIsoforms.py` (unmodified) on the same tmp_SS and seed."""
+    from dstep_synth import make_spliced_input
+    from mandalorion_b200.dstep import define_isoforms
+    work = str(tmp_path)
+    make_spliced_input(os.path.join(work, "tmp_SS"))
+    want_fa, want_r2i = run_unmodified_reference(work)
+    assert want_fa.count(b">") >= 8
+    out = os.path.join(work, "ours")
+    os.makedirs(out)
+    os.symlink(os.path.join(work, "tmp_SS"), os.path.join(out, "tmp_SS"))
+    np.random.seed(SEED)
+    n = define_isoforms(out, ctx=OracleBackedContext())
+    assert n == want_fa.count(b">")
+    assert open(os.path.join(out, "Isoform_Consensi.fasta"), "rb").read() == want_fa
+    assert open(os.path.join(out, "reads2isoforms.txt"), "rb").read() == want_r2i
+    if os.environ.get("REGEN_DSTEP_GOLDEN"):
+        os.makedirs(GOLD_SPLICED, exist_ok=True)
+        open(os.path.join(GOLD_SPLICED, "Isoform_Consensi.fasta"), "wb").write(want_fa)
+        open(os.path.join(GOLD_SPLICED, "reads2isoforms.txt"), "wb").write(want_r2i)
+    else:
+        assert open(os.path.join(GOLD_SPLICED, "Isoform_Consensi.fasta"), "rb").read() == want_fa
+        assert open(os.path.join(GOLD_SPLICED, "reads2isoforms.txt"), "rb").read() == want_r2i

@@ -199,3 +199,20 @@ def test_streaming_dispatch_on_the_gpu(gpu_ctx, monkeypatch):
     got = sc.finish()
     assert got == want and sc.n_batches >= 3
     assert sum(st["n_groups"] for st in sc.stats) == sum(1 for r in want if len(groups[int(r.split("~")[1]) // 1000]) > 2)
+
+
+def test_whole_dstep_on_the_gpu_matches_the_frozen_reference_run(gpu_ctx, tmp_path, monkeypatch):
+    """dstep.define_isoforms(): tmp_SS/*.psl (spliced genes on both strands, a non-canonical intron, mono-exonic
+    loci) -> group producer -> orientation -> streamed GPU batches -> writer.  The expected files were written by
+    the UNMODIFIED reference (`python3 defineIsoforms.py`, tests/test_dstep_reference.py) on the same input and
+    seed and are frozen under tests/golden/dstep_spliced/."""
+    from dstep_synth import make_spliced_input
+    from mandalorion_b200.dstep import define_isoforms
+    monkeypatch.setattr(cons_mod, "mappy_available", lambda: False)
+    make_spliced_input(str(tmp_path / "tmp_SS"))
+    np.random.seed(11)                                     # tests/test_dstep_reference.py: SEED
+    n = define_isoforms(str(tmp_path), ctx=gpu_ctx, batch_bases=60000)
+    gold = os.path.join(ROOT, "tests", "golden", "dstep_spliced")
+    assert n == 15
+    for f in ("Isoform_Consensi.fasta", "reads2isoforms.txt"):
+        assert open(os.path.join(str(tmp_path), f), "rb").read() == open(os.path.join(gold, f), "rb").read(), f
