@@ -230,14 +230,51 @@ def run_dstep(args):
     cpu_s = time.perf_counter() - t0
     got = [results[r]["1"][0] for r in prepared if not prepared[r]["1"].bypass]
     same = sum(1 for a, b in zip(got, want["cons"]) if not b or a == b.decode())
+    files = dstep_from_files(ctx, args)
     line = {"metric": "dstep_wall_seconds", "value": best["total_s"], "unit": "s", "higher_is_better": False, "n_gpus": 1,
             "config": {"workload": WORKLOADS["cfg1"][2] + ", random strand, through prepare_group -> finish_prepared -> "
                                    "write_isoform_files", "groups": n},
             "breakdown_s": best, "groups_per_s": n / best["total_s"],
             "orienter": "mappy" if C.mappy_available() else "mpoa_orient_batch (C++ seed-chain stage, %d threads)" % cores,
             "cpu_port": {"consensus_only_s": cpu_s, "cores": cores, "kind": "port", "note": PORT_NOTE},
-            "gpu_equals_port": same == len(got), "data": "synthetic"}
+            "gpu_equals_port": same == len(got), "data": "synthetic", "from_locus_files": files}
     print(json.dumps(line), flush=True)
+
+
+def dstep_from_files(ctx, args):
+    """The whole D step from tmp_SS/*.psl (BASELINE cfg5 shape at bench scale): group producer (locus.py) ->
+    prepare_group -> streamed GPU batches -> writer, i.e. dstep.define_isoforms(); the phases are host
+    seconds of the producing thread, `drain` is what was still running on the GPU after the last locus."""
+    from mandalorion_b200.dstep import define_isoforms
+    from mandalorion_b200.synth_loci import write_locus, write_spliced_locus
+    n_loci = max(4, (args.groups or 1000) // 40)
+    work = tempfile.mkdtemp(prefix="mpoa_dstep_files_")
+    tmp_ss = os.path.join(work, "tmp_SS")
+    os.makedirs(tmp_ss)
+    rng = np.random.Generator(np.random.PCG64(20261018 + 5))
+    t0 = time.perf_counter()
+    for k in range(n_loci):
+        chrom = "chr%d" % (1 + k % 5)
+        if k % 4 == 3:
+            write_locus(tmp_ss, chrom, 100000 * (k + 1), [(3000 * j, int(rng.integers(900, 1800)), int(rng.integers(3, 30)))
+                                                        for j in range(int(rng.integers(1, 5)))], rng, err=0.01)
+        else:
+            write_spliced_locus(tmp_ss, chrom, 100000 * (k + 1), rng, n_reads=int(rng.integers(40, 220)),
+                                n_exons=int(rng.integers(4, 9)), strand="+-"[k % 2], err=0.01)
+    gen_s = time.perf_counter() - t0
+    best = None
+    for rep in range(max(1, min(args.steps, 3))):
+        np.random.seed(20261018)
+        t0 = time.perf_counter()
+        n_iso = define_isoforms(work, ctx=ctx, workers=min(16, os.cpu_count() or 1))
+        total = time.perf_counter() - t0
+        cur = dict(define_isoforms.last_timings, total_s=total)
+        if best is None or total < best["total_s"]:
+            best = cur
+    best["isoforms_per_s"] = n_iso / best["total_s"]
+    best["input_generation_s"] = gen_s
+    best["workload"] = "%d loci (3/4 spliced genes with 4-8 exons and 40-220 reads, 1/4 mono-exonic), 1 %% error" % n_loci
+    return best
 
 
 def main():

@@ -107,11 +107,15 @@ struct Stager {
     }
 };
 
-/* expected band width of a group in cells: widest band row seen on calibration sets (oracle, every
- * named config) is never more than 2w+1 + length spread + two SIMD vectors of rounding */
+/* expected band width of a group in cells.  abPOA's band of a row spans the best column of its
+ * predecessors and the end-anchored diagonal, +-w, rounded outwards to whole SIMD vectors: measured with
+ * the oracle on every named config the widest row of a group is 2w+1 + 27..65 cells (median 43) whatever the
+ * read length, so 2w+1 + two vectors + 16 covers all but a fraction of a percent of the groups; the rest
+ * outgrow the level they were scheduled at and are re-run wider (ST_RETRY_WIDE).  Reads of very different
+ * lengths drift further from the diagonal: the spread beyond what the calibration sets had is added. */
 static int band_need(const mpoa_params &p, int maxlen, int minlen, bool seeded) {
     const int w = p.wb + (int)(p.wf * (float)maxlen);
-    int need = 2 * w + 1 + (maxlen - minlen) + 2 * p.simd_pn_i16;
+    int need = 2 * w + 1 + 2 * p.simd_pn_i16 + 16 + std::max(0, (maxlen - minlen) - 48);
     need = std::min(need, maxlen + 1 + 2 * p.simd_pn_i16);
     if (seeded) {
         /* `abpoa -S`: the band belongs to a window between two anchors (>= MPOA_SEED_MIN_W apart, rarely

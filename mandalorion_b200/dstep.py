@@ -123,9 +123,17 @@ def locus_roots(tmp_ss):
     return sorted(roots, key=lambda x: (x.split("~")[0], int(x.split("~")[1])))
 
 
+def _produce(job):
+    """One locus in a producer process: returns its groups and the RNG state the consensus step continues from."""
+    path, chrom, lb, rb, par, state = job
+    np.random.set_state(state)
+    groups = locus_groups(path, chrom, lb, rb, *par)
+    return groups, np.random.get_state()
+
+
 def define_isoforms(out_path, ctx=None, device=0, left_bounds=None, right_bounds=None, splice_site_width=1,
                     minimum_read_count=2, junctions=("gtag", "gcag", "atac", "ctac", "ctgc", "gtat"), cutoff=0.1,
-                    upstream_buffer=10, downstream_buffer=50, batch_bases=256 << 20, orient_threads=None):
+                    upstream_buffer=10, downstream_buffer=50, batch_bases=256 << 20, orient_threads=None, workers=0):
     """Module D (`defineIsoforms.py -p out_path ...`, reference defineIsoforms.py:93-168) on one GPU:
     reads out_path/tmp_SS/*.psl, writes out_path/Isoform_Consensi.fasta and reads2isoforms.txt.
 
@@ -135,12 +143,19 @@ def define_isoforms(out_path, ctx=None, device=0, left_bounds=None, right_bounds
 
     Random numbers: the reference forks one worker per locus, so every locus starts from the PARENT's
     NumPy RNG state; the same is done here (state saved at entry, restored before every locus), which makes
-    the output identical to a reference run started from the same state.  Returns the number of isoforms."""
+    the output identical to a reference run started from the same state.  workers > 0: the loci are parsed
+    and grouped by that many producer processes (spawned, so that no CUDA state is forked), consumed in locus
+    order while the GPU works on earlier loci; the result does not depend on it.  Returns the number of isoforms."""
+    import time
     tmp_ss = os.path.join(out_path, "tmp_SS")
     roots = locus_roots(tmp_ss)
     junctions = list(junctions)
     entry_state = np.random.get_state()
     sc = StreamingConsensus(ctx, device=device, batch_bases=batch_bases, orient_threads=orient_threads)
+    t = dict(producer=0.0, prepare=0.0, drain=0.0, write=0.0)
+    n_reads = 0
+    par = (splice_site_width, minimum_read_count, junctions, cutoff, upstream_buffer, downstream_buffer)
+    jobs = []
     for root in roots:
         chrom, start, end = root.split("~")
         start, end = int(start), int(end)
@@ -148,10 +163,34 @@ def define_isoforms(out_path, ctx=None, device=0, left_bounds=None, right_bounds
         for side, table in (("l", left_bounds), ("r", right_bounds)):
             per = (table or {}).get(chrom, {"5": [], "3": []})
             inside[side] = {k: [p for p in per[k] if start < p < end] for k in ("5", "3")}
-        np.random.set_state(entry_state)
-        groups = locus_groups(os.path.join(tmp_ss, root + ".psl"), chrom, inside["l"], inside["r"], splice_site_width,
-                              minimum_read_count, junctions, cutoff, upstream_buffer, downstream_buffer)
-        sc.add_locus(root, {isoform: prepare_group(reads) for isoform, reads in groups.items()})
-    results = sc.finish()
+        jobs.append((os.path.join(tmp_ss, root + ".psl"), chrom, inside["l"], inside["r"], par, entry_state))
+    pool = None
+    if workers > 0 and len(jobs) > 1:
+        import multiprocessing as mp
+        pool = mp.get_context("spawn").Pool(min(workers, len(jobs)))
+        produced = pool.imap(_produce, jobs, chunksize=1)
+    else:
+        produced = map(_produce, jobs)
+    try:
+        for root in roots:
+            t0 = time.perf_counter()
+            groups, state = next(produced)        # in-process: the work happens here; with a pool: the wait for it
+            t1 = time.perf_counter()
+            np.random.set_state(state)
+            sc.add_locus(root, {isoform: prepare_group(reads) for isoform, reads in groups.items()})
+            t["producer"] += t1 - t0
+            t["prepare"] += time.perf_counter() - t1
+            n_reads += sum(map(len, groups.values()))
+    finally:
+        if pool is not None:
+            pool.terminate()
+            pool.join()
+    t0 = time.perf_counter()
+    results = sc.finish()                 # what is still running on the GPU after the last locus was parsed
+    t1 = time.perf_counter()
+    n = write_isoform_files(roots, results, out_path)
+    t["drain"], t["write"] = t1 - t0, time.perf_counter() - t1
     define_isoforms.last_stats = sc.stats
-    return write_isoform_files(roots, results, out_path)
+    define_isoforms.last_timings = dict(t, loci=len(roots), reads_in_groups=n_reads, isoforms=n, batches=sc.n_batches,
+                                        producer_workers=workers)
+    return n

@@ -126,6 +126,11 @@ def test_whole_dstep_without_reference_code_on_the_path(tmp_path):
     assert n == want_fa.count(b">")
     assert open(os.path.join(out, "Isoform_Consensi.fasta"), "rb").read() == want_fa
     assert open(os.path.join(out, "reads2isoforms.txt"), "rb").read() == want_r2i
+    # producer processes (spawned) change nothing
+    np.random.seed(SEED)
+    assert define_isoforms(out, ctx=OracleBackedContext(), workers=2) == n
+    assert open(os.path.join(out, "Isoform_Consensi.fasta"), "rb").read() == want_fa
+    assert open(os.path.join(out, "reads2isoforms.txt"), "rb").read() == want_r2i
     if os.environ.get("REGEN_DSTEP_GOLDEN"):
         os.makedirs(GOLD_SPLICED, exist_ok=True)
         open(os.path.join(GOLD_SPLICED, "Isoform_Consensi.fasta"), "wb").write(want_fa)
