@@ -366,10 +366,14 @@ def main():
         ctx.consensus_batch(packed=(gro_p, rbo_p, bases_p), flags=flags)
     barrier()
     t0 = time.perf_counter()
+    e2e_parts = dict(kernel=0.0, h2d=0.0, d2h=0.0)
     for _ in range(args.steps):
         ctx.consensus_batch(packed=(gro_p, rbo_p, bases_p), flags=flags)
+        for k in e2e_parts:                                  # the library's own account of the call (CUDA events / host clock)
+            e2e_parts[k] += ctx.last_stats[k + "_ms"] / args.steps
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    e2e_parts["host_other"] = 1e3 * e2e_s / args.steps - sum(e2e_parts.values())
     h2d = int(gro_p.nbytes + rbo_p.nbytes + bases_p.nbytes)
     d2h = int(cons_bases + 4 * n_groups + 4 * n_groups)
 
@@ -441,7 +445,8 @@ def main():
             "groups_ok_frac": tot_ok / max(1.0, tot_groups),
             "seed_flagged_groups": int(stats.get("n_seed_groups", 0)), "seed_applied_groups": int(stats.get("n_seed_applied", 0)),
             "e2e": {"value": tot_groups * args.steps / (e2e_ms_max * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step_rank0": {k: round(v, 2) for k, v in e2e_parts.items()}},
             "gpu_launches": int(tot_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,

@@ -107,15 +107,15 @@ struct Stager {
     }
 };
 
-/* expected band width of a group in cells.  abPOA's band of a row spans the best column of its
- * predecessors and the end-anchored diagonal, +-w, rounded outwards to whole SIMD vectors: measured with
- * the oracle on every named config the widest row of a group is 2w+1 + 27..65 cells (median 43) whatever the
- * read length, so 2w+1 + two vectors + 16 covers all but a fraction of a percent of the groups; the rest
- * outgrow the level they were scheduled at and are re-run wider (ST_RETRY_WIDE).  Reads of very different
- * lengths drift further from the diagonal: the spread beyond what the calibration sets had is added. */
+/* expected band width of a group in cells: 2w+1 + length spread + two SIMD vectors of rounding.  Measured
+ * with the oracle on every named config the widest row of a group is 2w+1 + 27..65 cells (median 43), so
+ * this over-estimates by a median of 24 cells -- on purpose.  A tighter estimate (2w+1 + 48) moves half of
+ * cfg2's 256-cell work into the 128-cell kernel (-2.7 % kernel time), but the one group in ~10^4 that then
+ * outgrows its level is re-run ALONE in a later round, and one 50-read 4-kb group takes ~0.3 s on its single
+ * warp: the step gets slower, not faster (measured: 749 ms instead of 470 ms for 16 384 groups). */
 static int band_need(const mpoa_params &p, int maxlen, int minlen, bool seeded) {
     const int w = p.wb + (int)(p.wf * (float)maxlen);
-    int need = 2 * w + 1 + 2 * p.simd_pn_i16 + 16 + std::max(0, (maxlen - minlen) - 48);
+    int need = 2 * w + 1 + (maxlen - minlen) + 2 * p.simd_pn_i16;
     need = std::min(need, maxlen + 1 + 2 * p.simd_pn_i16);
     if (seeded) {
         /* `abpoa -S`: the band belongs to a window between two anchors (>= MPOA_SEED_MIN_W apart, rarely

@@ -6,6 +6,7 @@ computes a consensus itself and raises PoaError when the CUDA library or a GPU i
 """
 import ctypes as C
 import os
+import time
 from dataclasses import dataclass
 
 import numpy as np
@@ -304,7 +305,9 @@ class PoaContext:
         try:
             self.upload(gro, rbo, bases, flags)
             stats = self.run()
+            t0 = time.perf_counter()
             out = self.fetch(trace=trace)
+            stats["d2h_ms"] = 1e3 * (time.perf_counter() - t0)     # gather kernel + copies + the split into strings
         finally:
             self.set_trace(False)
         out["stats"] = stats
