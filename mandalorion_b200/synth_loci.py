@@ -142,6 +142,8 @@ def write_spliced_locus(path, chrom, locus_start, rng, n_reads=120, n_exons=5, s
         if rng.random() < 0.05 and len(ex) > 1:
             ex[0][1] += 1                                                               # junction off by one
         seq, cs, blocks = _cs_and_blocks(genome, [tuple(e) for e in ex], rng, err)
+        if not blocks:                   # a short single-exon isoform trimmed to nothing
+            continue
         tstart, tend = locus_start + blocks[0][0], locus_start + blocks[-1][0] + blocks[-1][1]
         start_min, end_max = min(start_min, tstart), max(end_max, tend)
         left_clip, right_clip = int(rng.integers(0, 12)), int(rng.integers(0, 12))

@@ -159,3 +159,22 @@ def test_cs_track_answers_like_a_walk_over_the_string():
     assert bases == "gtag"
     assert t.around(5000, 5001) == ("nnnn", b"", b"")
     assert t.around(1003, 1003) == ("nnnn", b"", b"")     # window holds no intron
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference is only present in the build container")
+@pytest.mark.parametrize("seed", range(8))
+def test_random_loci_and_parameters_against_the_unmodified_reference(seed, tmp_path):
+    """Random gene shapes, depths, error rates and D-step parameters (window, counts, cutoff, buffers)."""
+    rng = np.random.Generator(np.random.PCG64(1000 + seed))
+    extra = _mono_lines("chrR", 300, int(rng.integers(0, 8)), rng, "mono") if seed % 2 else []
+    root = write_spliced_locus(str(tmp_path), "chrR", int(rng.integers(1000, 500000)), rng, n_reads=int(rng.integers(20, 180)),
+                               n_exons=int(rng.integers(2, 8)), strand="+-"[seed % 2], err=float(rng.choice([0.005, 0.02, 0.05, 0.09])),
+                               noncanonical=None if seed % 3 else 1, extra_lines=extra)
+    par = dict(splice_site_width=int(rng.integers(1, 5)), minimum_read_count=int(rng.integers(1, 5)),
+               cutoff=float(rng.choice([0.01, 0.1, 0.3])), upstream_buffer=int(rng.integers(3, 15)),
+               downstream_buffer=int(rng.integers(10, 60)))
+    none = {"5": [], "3": []}
+    want, want_next = run_reference(str(tmp_path), root, "chrR", none, none, par)
+    got, got_next = run_ours(str(tmp_path), root, "chrR", none, none, par)
+    assert list(got) == list(want) and all(got[k] == want[k] for k in want)
+    assert got_next == want_next
