@@ -112,7 +112,9 @@ typedef struct mpoa_stats {
                                 ran the unseeded algorithm (see mpoa_seed_policy below)     */
     int64_t n_too_big_groups;/* groups that ended as MPOA_GROUP_TOO_BIG                    */
     int64_t max_band_width;  /* widest band row of the batch, cells (oracle only; 0 here)  */
-    int64_t reserved[4];
+    double  host_seed_ms;    /* host time of the `-S` minimizer seeding (inside h2d_ms for mpoa_batch_upload;
+                                beside the kernels of the unseeded groups for the one-call entry points) */
+    int64_t reserved[3];
 } mpoa_stats;
 
 /*

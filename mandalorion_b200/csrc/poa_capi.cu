@@ -158,6 +158,12 @@ struct mpoa_ctx {
     int32_t *d_anc_off = nullptr;
     int2 *d_anc = nullptr;
     int64_t n_seed_groups = 0;
+    /* anchors of the `abpoa -S` groups: computed inside the upload, or -- one-call entry points, where the
+     * caller's buffer stays valid -- by a host thread that runs beside the launches of the unseeded groups */
+    std::vector<int32_t> anc_off, anc;
+    std::thread seeder;
+    bool seed_pending = false;
+    double seed_ms = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t side = nullptr, side2 = nullptr;
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr, join2_ev = nullptr;
@@ -177,6 +183,8 @@ struct mpoa_ctx {
     } while (0)
 
 static void free_batch(mpoa_ctx *ctx) {   // forgets the uploaded batch; device buffers are kept for reuse
+    if (ctx->seeder.joinable()) ctx->seeder.join();
+    ctx->seed_pending = false;
     ctx->d_codes = nullptr; ctx->d_rbo = ctx->d_gro = ctx->d_region_off = nullptr; ctx->d_cons = nullptr;
     ctx->d_cons_len = ctx->d_status = ctx->d_queue = nullptr;
     ctx->d_tr_score = ctx->d_tr_bits = ctx->d_tr_aln = ctx->d_tr_node = nullptr; ctx->d_tr_cells = nullptr;
@@ -326,7 +334,8 @@ static bool is_pageable(const void *p) {
  * the caller's arrays): the context then holds a batch of n_sel groups numbered in sel order.
  */
 static int upload_impl(mpoa_ctx *ctx, int64_t n_all, const int64_t *group_read_off, const int64_t *read_base_off,
-                       const uint8_t *bases, const uint8_t *group_flags, int64_t n_sel, const int64_t *sel) {
+                       const uint8_t *bases, const uint8_t *group_flags, int64_t n_sel, const int64_t *sel,
+                       bool defer_seed = false) {
     if (!ctx || n_all < 0 || (sel && n_sel < 0)) return MPOA_EINVAL;
     if (n_all > 0 && (!group_read_off || !read_base_off)) { ctx->err = "null offsets"; return MPOA_EINVAL; }
     CK(cudaSetDevice(ctx->dev));
@@ -456,19 +465,31 @@ static int upload_impl(mpoa_ctx *ctx, int64_t n_all, const int64_t *group_read_o
     std::vector<int64_t> region(n_groups + 1);
     for (int64_t g = 0; g <= n_groups; ++g) region[g] = ctx->h_rbo[ctx->h_gro[g]];
     CKU(cudaMemcpyAsync(ctx->d_region_off, region.data(), (n_groups + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-    /* `abpoa -S` groups: their anchors are computed here, on the host threads, while the copies are in flight */
+    /* `abpoa -S` groups: their anchors are computed on the host threads while the copies are in flight */
     ctx->n_seed_groups = 0;
+    ctx->seed_ms = 0;
     for (uint8_t f : ctx->h_flags) ctx->n_seed_groups += (f & MPOA_FLAG_SEED) ? 1 : 0;
-    std::vector<int32_t> anc_off, anc;
     if (ctx->n_seed_groups > 0) {
-        const int nt = (int)std::max(1u, std::thread::hardware_concurrency());
-        seed_batch(n_groups, ctx->h_gro.data(), ctx->h_rbo.data(), bases, ctx->h_src.empty() ? nullptr : ctx->h_src.data(),
-                   ctx->h_flags.data(), MPOA_SEED_K, MPOA_SEED_W, MPOA_SEED_MIN_W, nt, anc_off, anc);
-        CKU(ctx->b_anc_off.ensure(anc_off.size() * sizeof(int32_t)));
-        CKU(ctx->b_anc.ensure(std::max<size_t>(anc.size(), 2) * sizeof(int32_t)));
+        /* anchors of a read are at least MPOA_SEED_MIN_W apart: the device buffers can be sized before they exist */
+        const size_t max_pairs = (size_t)(n_bases / MPOA_SEED_MIN_W + n_reads + 1);
+        CKU(ctx->b_anc_off.ensure(((size_t)n_reads + 1) * sizeof(int32_t)));
+        CKU(ctx->b_anc.ensure(max_pairs * 2 * sizeof(int32_t)));
         ctx->d_anc_off = (int32_t *)ctx->b_anc_off.p; ctx->d_anc = (int2 *)ctx->b_anc.p;
-        CKU(cudaMemcpyAsync(ctx->d_anc_off, anc_off.data(), anc_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-        if (!anc.empty()) CKU(cudaMemcpyAsync(ctx->d_anc, anc.data(), anc.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        auto seed = [ctx, n_groups, bases]() {
+            const auto t0 = std::chrono::steady_clock::now();
+            const int nt = (int)std::max(1u, std::thread::hardware_concurrency());
+            seed_batch(n_groups, ctx->h_gro.data(), ctx->h_rbo.data(), bases, ctx->h_src.empty() ? nullptr : ctx->h_src.data(),
+                       ctx->h_flags.data(), MPOA_SEED_K, MPOA_SEED_W, MPOA_SEED_MIN_W, nt, ctx->anc_off, ctx->anc);
+            ctx->seed_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        };
+        if (defer_seed) {
+            ctx->seed_pending = true;
+            ctx->seeder = std::thread(seed);          // joined by finish_seeding() before the first seeded launch
+        } else {
+            seed();
+            CKU(cudaMemcpyAsync(ctx->d_anc_off, ctx->anc_off.data(), ctx->anc_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+            if (!ctx->anc.empty()) CKU(cudaMemcpyAsync(ctx->d_anc, ctx->anc.data(), ctx->anc.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        }
     }
     join_copiers();
     for (int w = 0; w < Stager::K; ++w) CKU(copy_err[w]);
@@ -482,7 +503,7 @@ static int upload_impl(mpoa_ctx *ctx, int64_t n_all, const int64_t *group_read_o
         ctx->d_tr_cells = (long long *)ctx->b_tr_cells.p;
         ctx->d_tr_aln = (int32_t *)ctx->b_tr_aln.p; ctx->d_tr_node = (int32_t *)ctx->b_tr_node.p;
     }
-    CKU(cudaStreamSynchronize(ctx->stream));      // region / anc_off / anc are locals; the caller's buffer is free again
+    CKU(cudaStreamSynchronize(ctx->stream));      // region is a local; the caller's buffer is free again (unless seeding was deferred)
 #undef CKU
     ctx->h2d_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
     return MPOA_OK;
@@ -601,6 +622,17 @@ static void fill_args(mpoa_ctx *ctx, const Launch &ln, int k, KernelArgs &A) {
  * of SMs for as long as their longest group takes: they run beside the big ones on a second
  * stream, with their own workspace.  Groups that cannot be launched at all get ST_TOO_BIG.
  */
+/* deferred seeding: wait for the host thread and put the anchors in front of the seeded launch on its stream */
+static int finish_seeding(mpoa_ctx *ctx, cudaStream_t st) {
+    if (!ctx->seed_pending) return MPOA_OK;
+    if (ctx->seeder.joinable()) ctx->seeder.join();
+    ctx->seed_pending = false;
+    if (ctx->anc.size() > ctx->b_anc.cap / sizeof(int32_t)) { ctx->err = "anchor buffer too small"; return MPOA_EINVAL; }
+    CK(cudaMemcpyAsync(ctx->d_anc_off, ctx->anc_off.data(), ctx->anc_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (!ctx->anc.empty()) CK(cudaMemcpyAsync(ctx->d_anc, ctx->anc.data(), ctx->anc.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    return MPOA_OK;
+}
+
 static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_launch) {
     std::vector<Launch *> live;
     for (Launch &ln : launches) {
@@ -618,7 +650,12 @@ static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_la
         live.push_back(&ln);
     }
     if (live.empty()) return MPOA_OK;
-    std::sort(live.begin(), live.end(), [](const Launch *a, const Launch *b) { return a->lv > b->lv; });
+    /* widest first; while the anchors are still being computed on the host, everything unseeded goes first */
+    const bool seeds_late = ctx->seed_pending;
+    std::stable_sort(live.begin(), live.end(), [seeds_late](const Launch *a, const Launch *b) {
+        if (seeds_late && a->seeded != b->seeded) return !a->seeded;
+        return a->lv > b->lv;
+    });
     const size_t min_groups = (size_t)ctx->n_sm * 16;
     size_t n_big = 0;
     for (Launch *ln : live) { ln->small = ln->gs.size() < min_groups; n_big += ln->small ? 0 : 1; }
@@ -703,6 +740,7 @@ static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_la
             used_side2 = true;
         }
         if (!ln->small) first_big = false;
+        if (ln->seeded) { const int rc = finish_seeding(ctx, st); if (rc != MPOA_OK) return rc; }
         CK(launch_poa(ln->c.code(), A, (int)ln->n_blocks, ln->wpb, st));
         ++*n_launch;
         if (verbose)
@@ -859,6 +897,7 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
         pending.swap(next);
     }
     for (int32_t g : pending) ctx->h_status[g] = ST_TOO_BIG;  // still too big after the last attempt
+    { const int rc = finish_seeding(ctx, ctx->stream); if (rc != MPOA_OK) return rc; }   // no seeded launch was made
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
@@ -874,6 +913,7 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
     /* groups the reference would have run with `abpoa -S` (median read length >= 8000) */
     st.n_seed_groups = ctx->n_seed_groups;
     st.n_seed_applied = ctx->n_seed_groups;      // every kernel variant has its windowed instantiation
+    st.host_seed_ms = ctx->seed_ms;
     for (int64_t g = 0; g < ng; ++g) st.n_too_big_groups += ctx->h_status[g] == ST_TOO_BIG ? 1 : 0;
     ctx->last = st;
     ctx->ran = true;
@@ -935,8 +975,10 @@ extern "C" int mpoa_consensus_batch(mpoa_ctx *ctx, int64_t n_groups, const int64
     if (!ctx) return MPOA_EINVAL;
     const int saved = ctx->want_trace;
     if (trace) ctx->want_trace = 1;
-    int rc = mpoa_batch_upload(ctx, n_groups, group_read_off, read_base_off, bases, group_flags);
+    /* the caller's buffers stay valid until this call returns: the `-S` anchors are computed beside the kernels */
+    int rc = upload_impl(ctx, n_groups, group_read_off, read_base_off, bases, group_flags, 0, nullptr, true);
     if (rc == MPOA_OK) rc = mpoa_batch_run(ctx, nullptr);
+    if (ctx->seeder.joinable()) ctx->seeder.join();     // an error path may have left it running on the caller's buffer
     if (rc == MPOA_OK) rc = mpoa_batch_fetch(ctx, cons_off, cons_buf, cons_cap, group_status, trace);
     ctx->want_trace = saved;
     if (stats) *stats = ctx->last;
@@ -952,9 +994,10 @@ extern "C" int mpoa_shard_plan(int64_t n_groups, const int64_t *group_read_off, 
     if (p) dp = *p; else mpoa_default_params(&dp);
     if (dp.simd_pn_i16 <= 0) dp.simd_pn_i16 = 16;
     std::vector<double> cost(n_groups);
+    const int64_t n_reads = n_groups > 0 ? group_read_off[n_groups] : 0;
     for (int64_t g = 0; g < n_groups; ++g) {
         const int64_t r0 = group_read_off[g], r1 = group_read_off[g + 1];
-        if (r1 < r0) return MPOA_EINVAL;
+        if (r0 < 0 || r1 < r0 || r1 > n_reads) return MPOA_EINVAL;
         int64_t sum = 0, mx = 0, mn = INT64_MAX;
         for (int64_t r = r0; r < r1; ++r) {
             const int64_t len = read_base_off[r + 1] - read_base_off[r];
@@ -1012,8 +1055,9 @@ extern "C" int mpoa_consensus_batch_multi(mpoa_ctx *const *ctxs, int32_t n_ctx, 
         pt.off.assign(n + 1, 0);
         pt.status.assign(n, MPOA_GROUP_EMPTY);
         if (n == 0) { free_batch(ctx); return; }
-        pt.rc = upload_impl(ctx, n_groups, group_read_off, read_base_off, bases, group_flags, n, pt.sel.data());
+        pt.rc = upload_impl(ctx, n_groups, group_read_off, read_base_off, bases, group_flags, n, pt.sel.data(), true);
         if (pt.rc == MPOA_OK) pt.rc = mpoa_batch_run(ctx, nullptr);
+        if (ctx->seeder.joinable()) ctx->seeder.join();
         if (pt.rc != MPOA_OK) return;
         const int64_t cap = std::max<int64_t>(ctx->n_bases, 16);    // a consensus never outgrows its group's bases
         pt.buf.reset(new uint8_t[cap]);

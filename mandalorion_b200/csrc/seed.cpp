@@ -83,29 +83,82 @@ void forward_minimizers(const uint8_t *s, int n, int w, int k, std::vector<KmerA
 
 struct Pair { int32_t t, q; };
 
-void anchors_of(const std::vector<KmerAt> &prev_sorted, const std::vector<KmerAt> &cur, int k, int min_gap,
-                std::vector<Pair> &hits, std::vector<int32_t> &score, std::vector<int32_t> &from, std::vector<int32_t> &out) {
+/* The chaining step of hit i: among hits [first, i) the one that gives the best score (colinear, diagonal
+ * drift <= 100, a step scores min(k, advance)); it must beat k, the score of starting a chain at i; of
+ * equally good ones the nearest.  Candidate scores first (a branch-free loop the compiler vectorises: this is
+ * where the seeding spends its time), then the pick.  Returns the index or -1. */
+#if defined(__GNUC__) && defined(__x86_64__)
+__attribute__((target_clones("avx2", "default")))
+#endif
+int best_link(const int32_t *ht, const int32_t *hq, const int32_t *score, int first, int i, int k) {
+    int32_t cand[64];
+    const int m = i - first, ti = ht[i], qi = hq[i];
+    for (int x = 0; x < m; ++x) {
+        const int dt = ti - ht[first + x], dq = qi - hq[first + x];
+        const int drift = dt > dq ? dt - dq : dq - dt;
+        const int step = dt < dq ? dt : dq;
+        const bool ok = (dt > 0) & (dq > 0) & (drift <= 100);
+        cand[x] = ok ? score[first + x] + (step < k ? step : k) : INT32_MIN;
+    }
+    int best = INT32_MIN;
+    for (int x = 0; x < m; ++x) best = cand[x] > best ? cand[x] : best;
+    if (best <= k) return -1;
+    for (int x = m - 1; x >= 0; --x)                   // the nearest of the best: almost always one of the last few
+        if (cand[x] == best) return first + x;
+    return -1;
+}
+
+/* the minimizers of the previous read by hash: open addressing, up to 9 positions per hash kept in order
+ * of position (9 = "more than 8": such a hash is ignored) */
+struct KmerTable {
+    struct Slot { uint64_t h; int32_t n; int32_t end[9]; };
+    std::vector<Slot> slot;
+    uint64_t mask = 0;
+    void build(const std::vector<KmerAt> &ms) {
+        size_t cap = 64;
+        while (cap < 2 * ms.size() + 2) cap <<= 1;
+        slot.resize(cap);
+        mask = cap - 1;
+        for (Slot &x : slot) { x.h = UINT64_MAX; x.n = 0; }
+        for (const KmerAt &m : ms) {                    // ms is in order of position
+            uint64_t i = (m.h * 0x9E3779B97F4A7C15ULL >> 20) & mask;
+            while (slot[i].h != UINT64_MAX && slot[i].h != m.h) i = (i + 1) & mask;
+            Slot &x = slot[i];
+            x.h = m.h;
+            if (x.n < 9) x.end[x.n] = m.end;
+            if (x.n < 9) ++x.n;
+        }
+    }
+    const Slot *find(uint64_t h) const {
+        uint64_t i = (h * 0x9E3779B97F4A7C15ULL >> 20) & mask;
+        while (slot[i].h != UINT64_MAX) {
+            if (slot[i].h == h) return &slot[i];
+            i = (i + 1) & mask;
+        }
+        return nullptr;
+    }
+};
+
+void anchors_of(const KmerTable &prev, const std::vector<KmerAt> &cur, int k, int min_gap,
+                std::vector<Pair> &hits, std::vector<int32_t> &score, std::vector<int32_t> &from, std::vector<int32_t> &ht,
+                std::vector<int32_t> &hq, std::vector<int32_t> &out) {
     hits.clear();
     for (const KmerAt &m : cur) {
-        auto lo = std::lower_bound(prev_sorted.begin(), prev_sorted.end(), m.h, [](const KmerAt &a, uint64_t h) { return a.h < h; });
-        auto hi = lo;
-        while (hi != prev_sorted.end() && hi->h == m.h) ++hi;
-        if (hi - lo > 8) continue;
-        for (auto it = lo; it != hi; ++it) hits.push_back(Pair{it->end, m.end});
+        const KmerTable::Slot *x = prev.find(m.h);
+        if (!x || x->n > 8) continue;
+        for (int j = 0; j < x->n; ++j) hits.push_back(Pair{x->end[j], m.end});
     }
     std::sort(hits.begin(), hits.end(), [](const Pair &a, const Pair &b) { return a.t != b.t ? a.t < b.t : a.q < b.q; });
     const int n = (int)hits.size();
     if (n == 0) return;
     score.assign(n, k); from.assign(n, -1);
+    ht.resize(n); hq.resize(n);
+    for (int i = 0; i < n; ++i) { ht[i] = hits[i].t; hq[i] = hits[i].q; }
     int top = 0;
     for (int i = 0; i < n; ++i) {
         const int first = std::max(0, i - 64);
-        for (int j = i - 1; j >= first; --j) {
-            const int dt = hits[i].t - hits[j].t, dq = hits[i].q - hits[j].q;
-            if (dt <= 0 || dq <= 0 || std::abs(dt - dq) > 100) continue;
-            const int cand = score[j] + std::min(k, std::min(dt, dq));
-            if (cand > score[i]) { score[i] = cand; from[i] = j; }
-        }
+        const int j = best_link(ht.data(), hq.data(), score.data(), first, i, k);
+        if (j >= 0) { from[i] = j; score[i] = score[j] + std::min(k, std::min(ht[i] - ht[j], hq[i] - hq[j])); }
         if (score[i] > score[top]) top = i;
     }
     std::vector<int32_t> path;
@@ -135,25 +188,21 @@ void seed_batch(int64_t n_groups, const int64_t *gro, const int64_t *rbo, const 
     std::vector<std::vector<int32_t>> per_read((size_t)n_reads);
     std::atomic<int64_t> next(0);
     auto worker = [&]() {
-        std::vector<KmerAt> a, b;
+        std::vector<KmerAt> cur;
+        KmerTable prev;
         std::vector<Pair> hits;
-        std::vector<int32_t> score, from;
+        std::vector<int32_t> score, from, ht, hq;
         for (;;) {
             const int64_t g = next.fetch_add(1);
             if (g >= n_groups) break;
             if (!flags || !(flags[g] & 1)) continue;
-            std::vector<KmerAt> *prev = &a, *cur = &b;
             int64_t prev_r = -1;
             for (int64_t r = gro[g]; r < gro[g + 1]; ++r) {
                 const int len = (int)(rbo[r + 1] - rbo[r]);
                 if (len <= 0) continue;                 // an empty read is skipped by the aligner too
-                forward_minimizers(bases + (src_off ? src_off[r] : rbo[r]), len, w, k, *cur);
-                if (prev_r >= 0) {
-                    /* *prev is already sorted by hash */
-                    anchors_of(*prev, *cur, k, min_gap, hits, score, from, per_read[(size_t)r]);
-                }
-                std::sort(cur->begin(), cur->end(), [](const KmerAt &x, const KmerAt &y) { return x.h != y.h ? x.h < y.h : x.end < y.end; });
-                std::swap(prev, cur);
+                forward_minimizers(bases + (src_off ? src_off[r] : rbo[r]), len, w, k, cur);
+                if (prev_r >= 0) anchors_of(prev, cur, k, min_gap, hits, score, from, ht, hq, per_read[(size_t)r]);
+                prev.build(cur);
                 prev_r = r;
             }
         }

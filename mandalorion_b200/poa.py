@@ -37,7 +37,7 @@ class _Stats(C.Structure):
                 ("n_retry_groups", C.c_int64), ("kernel_ms", C.c_double), ("h2d_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("n_kernel_launches", C.c_int64), ("phase_cycles", C.c_int64 * 6),
                 ("n_seed_groups", C.c_int64), ("n_seed_applied", C.c_int64), ("n_too_big_groups", C.c_int64),
-                ("max_band_width", C.c_int64), ("reserved", C.c_int64 * 4)]
+                ("max_band_width", C.c_int64), ("host_seed_ms", C.c_double), ("reserved", C.c_int64 * 3)]
 
 
 class _Trace(C.Structure):
@@ -299,16 +299,31 @@ class PoaContext:
         """groups: list of lists of reads (str/bytes), aligned in the given order; flags: MPOA_FLAG_* per
         group.  Returns dict(cons=[bytes], status=int32[], stats=dict, trace=dict|None)."""
         gro, rbo, bases = packed if packed is not None else pack_groups(groups)
+        gro = np.ascontiguousarray(gro, dtype=np.int64)
+        rbo = np.ascontiguousarray(rbo, dtype=np.int64)
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
         if flags is not None:
             flags = np.ascontiguousarray(flags, dtype=np.uint8)
-        self.set_trace(trace)
-        try:
-            self.upload(gro, rbo, bases, flags)
-            stats = self.run()
-            t0 = time.perf_counter()
-            out = self.fetch(trace=trace)
-            stats["d2h_ms"] = 1e3 * (time.perf_counter() - t0)     # gather kernel + copies + the split into strings
-        finally:
-            self.set_trace(False)
-        out["stats"] = stats
-        return out
+        ng, nr = len(gro) - 1, len(rbo) - 1
+        nb = int(rbo[-1]) if len(rbo) else 0
+        cap = max(16, nb)                                   # a consensus never outgrows its group's bases
+        cons_buf = np.empty(cap, dtype=np.uint8)
+        cons_off = np.zeros(ng + 1, dtype=np.int64)
+        status = np.zeros(ng, dtype=np.int32)
+        tr, arrs = None, None
+        if trace:
+            arrs = dict(read_score=np.zeros(nr, np.int32), read_bits=np.zeros(nr, np.int32),
+                        read_band_cells=np.zeros(nr, np.int64), base_aln=np.full(nb, -9, np.int32),
+                        base_node=np.full(nb, -9, np.int32))
+            tr = _Trace(*[arrs[k].ctypes.data for k in
+                          ("read_score", "read_bits", "read_band_cells", "base_aln", "base_node")])
+        st = _Stats()
+        # ONE C call (upload -> kernels -> fetch): the library knows the buffers stay valid and overlaps the
+        # host-side `-S` seeding with the kernels of the unseeded groups
+        self._check(self._lib.mpoa_consensus_batch(self._h, ng, _ptr(gro), _ptr(rbo), _ptr(bases), _ptr(flags),
+                                                   _ptr(cons_off), _ptr(cons_buf), cap, _ptr(status), C.byref(st),
+                                                   C.byref(tr) if tr is not None else None), "mpoa_consensus_batch")
+        self._n = (ng, nr, nb)
+        self.last_stats = self._stats_dict(st)
+        return dict(cons=_split(cons_buf[:cons_off[ng]].tobytes(), cons_off), status=status, cons_off=cons_off,
+                    trace=arrs, stats=self.last_stats)
