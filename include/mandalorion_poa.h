@@ -114,7 +114,9 @@ typedef struct mpoa_stats {
     int64_t max_band_width;  /* widest band row of the batch, cells (oracle only; 0 here)  */
     double  host_seed_ms;    /* host time of the `-S` minimizer seeding (inside h2d_ms for mpoa_batch_upload;
                                 beside the kernels of the unseeded groups for the one-call entry points) */
-    int64_t reserved[3];
+    double  kernel_wait_ms;  /* time mpoa_batch_run waited for another context's kernel phase on the same device
+                                (contexts of one process take turns on the SMs; poa.PoaPipeline) */
+    int64_t reserved[2];
 } mpoa_stats;
 
 /*
@@ -142,7 +144,9 @@ int  mpoa_create(mpoa_ctx **out, int device_ordinal, const mpoa_params *p);
 void mpoa_destroy(mpoa_ctx *ctx);
 const char *mpoa_last_error(mpoa_ctx *ctx);
 
-/* Kernels are launched on this stream (a cudaStream_t); default is the legacy stream. */
+/* Kernels are launched on this stream (a cudaStream_t).  Default: a non-blocking stream the context owns, so
+ * that several contexts on one GPU (mandalorion_b200.poa.PoaPipeline: one batch uploads while another one
+ * computes) never serialise on the legacy stream.  Every entry point returns with its own work finished. */
 int  mpoa_set_stream(mpoa_ctx *ctx, void *cuda_stream);
 
 /* enable != 0: the next mpoa_batch_upload() also allocates the per-read trace arrays. */

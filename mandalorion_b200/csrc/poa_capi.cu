@@ -8,12 +8,14 @@
  * of the reference (utils/SpliceDefineConsensus.py:917), one per group.
  */
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -26,9 +28,9 @@ namespace mpoa {
 cudaError_t launch_encode(const uint8_t *ascii, uint8_t *codes, int64_t n, cudaStream_t stream);
 cudaError_t launch_poa(int code, const KernelArgs &A, int n_blocks, int warps_per_block, cudaStream_t stream);
 int poa_max_blocks_per_sm(int code, int wcap, int warps_per_block, bool seeded);
-void seed_batch(int64_t n_groups, const int64_t *gro, const int64_t *rbo, const uint8_t *bases, const int64_t *src_off,
-                const uint8_t *flags, int k, int w, int min_gap, int n_threads, std::vector<int32_t> &anc_off,
-                std::vector<int32_t> &anc);
+void seed_batch(const int64_t *gro, const int64_t *rbo, const uint8_t *bases, const int64_t *src_off,
+                const int32_t *order, int64_t n_order, int64_t chunk_size, std::atomic<int64_t> *done,
+                int k, int w, int min_gap, int n_threads, const int32_t *anc_off, int32_t *anc);
 size_t poa_smem_bytes(int code, int wcap, int warps_per_block);
 bool variant_exists(int code);
 cudaError_t launch_int_peak(uint32_t *out, int blocks, int iters, cudaStream_t stream);
@@ -128,11 +130,55 @@ static int band_need(const mpoa_params &p, int maxlen, int minlen, bool seeded) 
     return need;
 }
 
+/* launch levels: kernel variant (team size T, words per lane WPL of the packed int16x2 DP; WPL 0 =
+ * int32 lanes) and the band capacity in cells.  A group escalates along this list when its band
+ * or its scores outgrow the level it ran at.  The int32 ring (RING x 3 x wcap ints per warp) limits
+ * the widest band to 4096 cells; wider groups are reported as MPOA_GROUP_TOO_BIG. */
+struct Level { int T, WPL, wcap; };
+static const Level kLevels[] = {{32, 2, 128}, {32, 4, 256}, {32, 8, 512},
+                                {32, 0, 256}, {32, 0, 512}, {32, 0, 1024}, {32, 0, 2048}, {32, 0, 4096}};
+static const int kNumLevels = (int)(sizeof(kLevels) / sizeof(kLevels[0]));
+
+/* tuning aid: bit l set = packed level l may be scheduled (default: all) */
+static unsigned level_mask_env() {
+    if (const char *ml = getenv("MPOA_LEVELS")) return (unsigned)strtoul(ml, nullptr, 0) | ~0x7u;
+    return ~0u;
+}
+/* narrowest level that holds a band of wneed cells */
+static int pick_level(const mpoa_params &p, unsigned level_mask, bool lanes16, int wneed) {
+    for (int l = 0; l < kNumLevels; ++l) {
+        if (!((level_mask >> l) & 1u)) continue;
+        if (kLevels[l].WPL != 0 && !lanes16) continue;
+        /* a lane wider than abPOA's vector length may start up to (2*WPL - pn) cells before the band */
+        const int slack = std::max(0, 2 * kLevels[l].WPL - p.simd_pn_i32);
+        if (kLevels[l].wcap >= wneed + slack) return l;
+    }
+    return kNumLevels - 1;
+}
+
+/*
+ * What the contexts of one process share per device: the kernels of two contexts never run side by side
+ * (different kernel variants resident on the same SMs were measured at 1.5x the time of the same work back to
+ * back -- they evict each other from the instruction cache), so the kernel phase of mpoa_batch_run holds `mu`,
+ * and the workspace of the resident teams (tens of GB) exists once per device, not once per context.  The
+ * copies and host passes of one context's batch run beside the kernels of another (poa.PoaPipeline).
+ */
+struct DevShared {
+    std::mutex mu;
+    uint8_t *ws = nullptr;
+    size_t ws_bytes = 0;
+    int users = 0;
+};
+static DevShared g_dev[64];
+static std::mutex g_dev_users;
+static std::mutex g_seed_mu;                   // host-side `-S` seeding: one batch at a time (it uses all host threads)
+
 struct mpoa_ctx {
     int dev = 0;
     int n_sm = 0;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;         // non-blocking: contexts of one process never serialise on the legacy stream
     mpoa_params params;
     std::string err;
     int want_trace = 0;
@@ -151,23 +197,31 @@ struct mpoa_ctx {
     unsigned long long *d_stats = nullptr;
     int32_t *d_tr_score = nullptr, *d_tr_bits = nullptr, *d_tr_aln = nullptr, *d_tr_node = nullptr;
     long long *d_tr_cells = nullptr;
-    uint8_t *d_ws = nullptr;
-    size_t ws_bytes = 0;
     DevBuf b_ascii, b_codes, b_rbo, b_gro, b_region, b_len, b_status, b_queue, b_out_off, b_out;
-    DevBuf b_tr_score, b_tr_bits, b_tr_cells, b_tr_aln, b_tr_node, b_anc_off, b_anc;
-    int32_t *d_anc_off = nullptr;
+    DevBuf b_tr_score, b_tr_bits, b_tr_cells, b_tr_aln, b_tr_node, b_anc_off, b_anc, b_seed_rank, b_seed_ready;
+    int32_t *d_anc_off = nullptr, *d_seed_rank = nullptr, *d_seed_ready = nullptr;
     int2 *d_anc = nullptr;
     int64_t n_seed_groups = 0;
     /* anchors of the `abpoa -S` groups: computed inside the upload, or -- one-call entry points, where the
-     * caller's buffer stays valid -- by a host thread that runs beside the launches of the unseeded groups */
-    std::vector<int32_t> anc_off, anc;
+     * caller's buffer stays valid -- by host threads that run beside the kernels.  The groups are seeded in the
+     * order the launches ask for them (seed_order); the arena (h_anc, two ints per slot, region of read r at slot
+     * h_anc_off[r]) is laid out in that order, so that a finished chunk of groups is one contiguous copy; the
+     * device learns of it through the counter d_seed_ready (publish_seeds). */
+    std::vector<int32_t> h_anc_off, h_anc, seed_order, seed_rank, ready_vals;
+    std::vector<int64_t> chunk_slot;           // first arena slot of every chunk (+ the end)
+    int64_t seed_chunk = 0, n_seed_chunks = 0;
+    std::unique_ptr<std::atomic<int64_t>[]> seed_done;
+    cudaStream_t pub = nullptr;                // the anchor copies: beside the running kernels
     std::thread seeder;
     bool seed_pending = false;
-    double seed_ms = 0;
+    double seed_ms = 0, seed_wait_ms = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t side = nullptr, side2 = nullptr;
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr, join2_ev = nullptr;
     double h2d_ms = 0;
+    uint8_t *d_ascii = nullptr;
+    bool need_encode = false;                  // the uploaded bases are still ASCII
+    std::vector<int64_t> h_cons_off;           // consensus offsets of the last run (compact buffer b_out)
     bool ran = false;
     std::vector<int32_t> h_status;
     mpoa_stats last;
@@ -189,14 +243,14 @@ static void free_batch(mpoa_ctx *ctx) {   // forgets the uploaded batch; device 
     ctx->d_cons_len = ctx->d_status = ctx->d_queue = nullptr;
     ctx->d_tr_score = ctx->d_tr_bits = ctx->d_tr_aln = ctx->d_tr_node = nullptr; ctx->d_tr_cells = nullptr;
     ctx->n_groups = ctx->n_reads = ctx->n_bases = 0;
-    ctx->d_anc_off = nullptr; ctx->d_anc = nullptr; ctx->n_seed_groups = 0;
+    ctx->d_anc_off = nullptr; ctx->d_anc = nullptr; ctx->d_seed_rank = ctx->d_seed_ready = nullptr; ctx->n_seed_groups = 0;
     ctx->ran = false;
 }
 
 static void release_buffers(mpoa_ctx *ctx) {
     for (DevBuf *b : {&ctx->b_ascii, &ctx->b_codes, &ctx->b_rbo, &ctx->b_gro, &ctx->b_region, &ctx->b_len, &ctx->b_status,
                       &ctx->b_queue, &ctx->b_out_off, &ctx->b_out, &ctx->b_tr_score, &ctx->b_tr_bits, &ctx->b_tr_cells,
-                      &ctx->b_tr_aln, &ctx->b_tr_node, &ctx->b_anc_off, &ctx->b_anc})
+                      &ctx->b_tr_aln, &ctx->b_tr_node, &ctx->b_anc_off, &ctx->b_anc, &ctx->b_seed_rank, &ctx->b_seed_ready})
         b->release();
 }
 
@@ -216,7 +270,7 @@ extern "C" int mpoa_create(mpoa_ctx **out, int device_ordinal, const mpoa_params
     *out = nullptr;
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) return MPOA_ENODEV;
-    if (device_ordinal < 0 || device_ordinal >= n_dev) return MPOA_ENODEV;
+    if (device_ordinal < 0 || device_ordinal >= n_dev || device_ordinal >= 64) return MPOA_ENODEV;
     if (cudaSetDevice(device_ordinal) != cudaSuccess) return MPOA_ENODEV;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess) return MPOA_ENODEV;
@@ -230,10 +284,13 @@ extern "C" int mpoa_create(mpoa_ctx **out, int device_ordinal, const mpoa_params
     if (ctx->params.simd_pn_i32 <= 0) ctx->params.simd_pn_i32 = 8;
     if (cudaMalloc(&ctx->d_queue_head, 16 * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&ctx->d_stats, SI_COUNT * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
         return MPOA_ENODEV;
     }
+    ctx->stream = ctx->own_stream;
+    { std::lock_guard<std::mutex> g(g_dev_users); ++g_dev[ctx->dev].users; }
     *out = ctx;
     return MPOA_OK;
 }
@@ -243,7 +300,15 @@ extern "C" void mpoa_destroy(mpoa_ctx *ctx) {
     cudaSetDevice(ctx->dev);
     free_batch(ctx);
     release_buffers(ctx);
-    cudaFree(ctx->d_ws);
+    {
+        std::lock_guard<std::mutex> g(g_dev_users);
+        DevShared &D = g_dev[ctx->dev];
+        if (--D.users == 0) {                         // the last context of this device takes the workspace with it
+            std::lock_guard<std::mutex> k(D.mu);
+            cudaFree(D.ws);
+            D.ws = nullptr; D.ws_bytes = 0;
+        }
+    }
     cudaFree(ctx->d_queue_head);
     cudaFree(ctx->d_stats);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -253,6 +318,8 @@ extern "C" void mpoa_destroy(mpoa_ctx *ctx) {
     if (ctx->join2_ev) cudaEventDestroy(ctx->join2_ev);
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->side2) cudaStreamDestroy(ctx->side2);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->pub) cudaStreamDestroy(ctx->pub);
     ctx->stager.release();
     delete ctx;
 }
@@ -470,30 +537,80 @@ static int upload_impl(mpoa_ctx *ctx, int64_t n_all, const int64_t *group_read_o
     ctx->seed_ms = 0;
     for (uint8_t f : ctx->h_flags) ctx->n_seed_groups += (f & MPOA_FLAG_SEED) ? 1 : 0;
     if (ctx->n_seed_groups > 0) {
-        /* anchors of a read are at least MPOA_SEED_MIN_W apart: the device buffers can be sized before they exist */
-        const size_t max_pairs = (size_t)(n_bases / MPOA_SEED_MIN_W + n_reads + 1);
+        /* seeding order = launch order: widest level first, heaviest group first (run_round, mpoa_batch_run) */
+        const unsigned lmask = level_mask_env();
+        std::vector<int32_t> &order = ctx->seed_order;
+        order.clear();
+        std::vector<int8_t> lvl(n_groups, 0);
+        for (int64_t g = 0; g < n_groups; ++g)
+            if (ctx->h_flags[g] & MPOA_FLAG_SEED) {
+                order.push_back((int32_t)g);
+                lvl[g] = (int8_t)pick_level(ctx->params, lmask, true, ctx->params.debug_small_caps ? 1 : ctx->ginfo[g].wneed);
+            }
+        std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+            if (lvl[a] != lvl[b]) return lvl[a] > lvl[b];
+            const GroupInfo &ga = ctx->ginfo[a], &gb = ctx->ginfo[b];
+            return ga.cost != gb.cost ? ga.cost > gb.cost : a < b;
+        });
+        const int64_t n_order = (int64_t)order.size();
+        ctx->seed_rank.assign(n_groups, -1);                 // unflagged groups never wait
+        for (int64_t i = 0; i < n_order; ++i) ctx->seed_rank[order[i]] = (int32_t)i;
+        /* anchors of a read are at least MPOA_SEED_MIN_W apart: its region can be laid out before they exist */
+        ctx->seed_chunk = std::min<int64_t>(256, std::max<int64_t>(8, n_order / 64));
+        ctx->n_seed_chunks = (n_order + ctx->seed_chunk - 1) / ctx->seed_chunk;
+        ctx->chunk_slot.assign(ctx->n_seed_chunks + 1, 0);
+        ctx->h_anc_off.assign((size_t)n_reads + 1, 0);
+        int64_t slot = 0;
+        for (int64_t i = 0; i < n_order; ++i) {
+            if (i % ctx->seed_chunk == 0) ctx->chunk_slot[i / ctx->seed_chunk] = slot;
+            const int64_t g = order[i];
+            for (int64_t r = ctx->h_gro[g]; r < ctx->h_gro[g + 1]; ++r) {
+                ctx->h_anc_off[r] = (int32_t)slot;
+                slot += (ctx->h_rbo[r + 1] - ctx->h_rbo[r]) / MPOA_SEED_MIN_W + 2;
+            }
+        }
+        ctx->chunk_slot[ctx->n_seed_chunks] = slot;
+        if (slot > INT_MAX / 2) return fail(MPOA_EINVAL, "too many seeded bases in one batch");
+        ctx->h_anc.resize((size_t)slot * 2);
+        ctx->seed_done.reset(new std::atomic<int64_t>[ctx->n_seed_chunks]);
+        for (int64_t c = 0; c < ctx->n_seed_chunks; ++c) ctx->seed_done[c].store(0);
+        ctx->ready_vals.assign(ctx->n_seed_chunks, 0);
         CKU(ctx->b_anc_off.ensure(((size_t)n_reads + 1) * sizeof(int32_t)));
-        CKU(ctx->b_anc.ensure(max_pairs * 2 * sizeof(int32_t)));
+        CKU(ctx->b_anc.ensure(((size_t)slot + 1) * 2 * sizeof(int32_t)));
+        CKU(ctx->b_seed_rank.ensure((size_t)n_groups * sizeof(int32_t)));
+        CKU(ctx->b_seed_ready.ensure(sizeof(int32_t)));
         ctx->d_anc_off = (int32_t *)ctx->b_anc_off.p; ctx->d_anc = (int2 *)ctx->b_anc.p;
-        auto seed = [ctx, n_groups, bases]() {
+        ctx->d_seed_rank = (int32_t *)ctx->b_seed_rank.p; ctx->d_seed_ready = (int32_t *)ctx->b_seed_ready.p;
+        CKU(cudaMemcpyAsync(ctx->d_anc_off, ctx->h_anc_off.data(), (size_t)n_reads * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CKU(cudaMemcpyAsync(ctx->d_seed_rank, ctx->seed_rank.data(), (size_t)n_groups * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CKU(cudaMemsetAsync(ctx->d_seed_ready, 0, sizeof(int32_t), ctx->stream));
+        ctx->seed_wait_ms = 0;
+        auto seed = [ctx, n_order, bases, defer_seed]() {
+            /* one batch at a time: the seeding of the batch whose kernels are running is on the critical path and
+             * uses every host thread; the next batch's (PoaPipeline) starts when it is done */
+            std::lock_guard<std::mutex> one_at_a_time(g_seed_mu);
             const auto t0 = std::chrono::steady_clock::now();
             const int nt = (int)std::max(1u, std::thread::hardware_concurrency());
-            seed_batch(n_groups, ctx->h_gro.data(), ctx->h_rbo.data(), bases, ctx->h_src.empty() ? nullptr : ctx->h_src.data(),
-                       ctx->h_flags.data(), MPOA_SEED_K, MPOA_SEED_W, MPOA_SEED_MIN_W, nt, ctx->anc_off, ctx->anc);
+            seed_batch(ctx->h_gro.data(), ctx->h_rbo.data(), bases, ctx->h_src.empty() ? nullptr : ctx->h_src.data(),
+                       ctx->seed_order.data(), n_order, ctx->seed_chunk, defer_seed ? ctx->seed_done.get() : nullptr,
+                       MPOA_SEED_K, MPOA_SEED_W, MPOA_SEED_MIN_W, nt, ctx->h_anc_off.data(), ctx->h_anc.data());
             ctx->seed_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         };
         if (defer_seed) {
             ctx->seed_pending = true;
-            ctx->seeder = std::thread(seed);          // joined by finish_seeding() before the first seeded launch
+            ctx->seeder = std::thread(seed);          // its chunks are published by publish_seeds() while the kernels run
         } else {
             seed();
-            CKU(cudaMemcpyAsync(ctx->d_anc_off, ctx->anc_off.data(), ctx->anc_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-            if (!ctx->anc.empty()) CKU(cudaMemcpyAsync(ctx->d_anc, ctx->anc.data(), ctx->anc.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+            if (slot > 0) CKU(cudaMemcpyAsync(ctx->d_anc, ctx->h_anc.data(), (size_t)slot * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
         }
     }
     join_copiers();
     for (int w = 0; w < Stager::K; ++w) CKU(copy_err[w]);
-    CKU(launch_encode(d_ascii, ctx->d_codes, n_bases, ctx->stream));
+    /* the bases are encoded (ASCII -> nt4) by the first mpoa_batch_run, inside its kernel phase: while the
+     * persistent kernels of another context's batch hold the SMs, a kernel launched here would wait for them --
+     * and the upload, which is meant to run BESIDE them, with it */
+    ctx->d_ascii = d_ascii;
+    ctx->need_encode = true;
     if (ctx->want_trace) {
         const size_t nr = (size_t)std::max<int64_t>(n_reads, 1);
         CKU(ctx->b_tr_score.ensure(nr * sizeof(int32_t))); CKU(ctx->b_tr_bits.ensure(nr * sizeof(int32_t)));
@@ -559,15 +676,6 @@ static SlotLayout make_layout(const Caps &c, bool seeded) {
     return L;
 }
 
-/* launch levels: kernel variant (team size T, words per lane WPL of the packed int16x2 DP; WPL 0 =
- * int32 lanes) and the band capacity in cells.  A group escalates along this list when its band
- * or its scores outgrow the level it ran at.  The int32 ring (RING x 3 x wcap ints per warp) limits
- * the widest band to 4096 cells; wider groups are reported as MPOA_GROUP_TOO_BIG. */
-struct Level { int T, WPL, wcap; };
-static const Level kLevels[] = {{32, 2, 128}, {32, 4, 256}, {32, 8, 512},
-                                {32, 0, 256}, {32, 0, 512}, {32, 0, 1024}, {32, 0, 2048}, {32, 0, 4096}};
-static const int kNumLevels = (int)(sizeof(kLevels) / sizeof(kLevels[0]));
-
 /* one kernel launch of a round: the groups of one level with one set of capacities */
 struct Launch {
     int lv = 0;
@@ -588,13 +696,17 @@ static void fill_args(mpoa_ctx *ctx, const Launch &ln, int k, KernelArgs &A) {
     std::memset(&A, 0, sizeof(A));
     A.codes = ctx->d_codes; A.read_off = ctx->d_rbo; A.group_read_off = ctx->d_gro;
     A.queue = ctx->d_queue + ln.q_off; A.n_queue = (int)ln.gs.size(); A.queue_head = ctx->d_queue_head + k;
-    A.ws = ctx->d_ws + ln.ws_off; A.L = ln.L;
+    A.ws = g_dev[ctx->dev].ws + ln.ws_off; A.L = ln.L;
     A.cons = ctx->d_cons; A.cons_off = ctx->d_region_off; A.cons_len = ctx->d_cons_len; A.status = ctx->d_status;
     A.stats = ctx->d_stats;
     A.tr_score = ctx->d_tr_score; A.tr_bits = ctx->d_tr_bits; A.tr_cells = ctx->d_tr_cells;
     A.tr_aln = ctx->d_tr_aln; A.tr_node = ctx->d_tr_node;
     A.level = ln.lv;
-    if (ln.seeded) { A.anc_off = ctx->d_anc_off; A.anc = ctx->d_anc; A.seed_k = MPOA_SEED_K; }
+    if (ln.seeded) {
+        A.anc_off = ctx->d_anc_off; A.anc = ctx->d_anc; A.seed_k = MPOA_SEED_K;
+        A.seed_rank = ctx->d_seed_rank;
+        A.seed_ready = ctx->seed_pending ? ctx->d_seed_ready : nullptr;     // anchors still being computed: groups wait for theirs
+    }
     A.tbcap_words = (uint32_t)std::min<uint64_t>(ln.L.tbcap / 4, 0xfffff000ull);
     const mpoa_params &p = ctx->params;
     A.P.match = std::abs(p.match); A.P.mismatch = std::abs(p.mismatch);
@@ -622,14 +734,29 @@ static void fill_args(mpoa_ctx *ctx, const Launch &ln, int k, KernelArgs &A) {
  * of SMs for as long as their longest group takes: they run beside the big ones on a second
  * stream, with their own workspace.  Groups that cannot be launched at all get ST_TOO_BIG.
  */
-/* deferred seeding: wait for the host thread and put the anchors in front of the seeded launch on its stream */
-static int finish_seeding(mpoa_ctx *ctx, cudaStream_t st) {
+/*
+ * Deferred seeding: the seeded launches are already on the device, every group waiting for its rank in the
+ * seeding order (poa_group_kernel).  Chunk after chunk, as the host threads finish them: copy the chunk's slice
+ * of the arena, then the new value of the counter, on a stream of their own -- the copies run beside the kernels.
+ */
+static int publish_seeds(mpoa_ctx *ctx) {
     if (!ctx->seed_pending) return MPOA_OK;
+    if (!ctx->pub) CK(cudaStreamCreateWithFlags(&ctx->pub, cudaStreamNonBlocking));
+    const int64_t n_order = (int64_t)ctx->seed_order.size();
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int64_t c = 0; c < ctx->n_seed_chunks; ++c) {
+        const int64_t want = std::min(ctx->seed_chunk, n_order - c * ctx->seed_chunk);
+        while (ctx->seed_done[c].load(std::memory_order_acquire) < want) std::this_thread::sleep_for(std::chrono::microseconds(100));
+        const int64_t lo = ctx->chunk_slot[c], hi = ctx->chunk_slot[c + 1];
+        if (hi > lo)
+            CK(cudaMemcpyAsync(ctx->d_anc + lo, ctx->h_anc.data() + 2 * lo, (size_t)(hi - lo) * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->pub));
+        ctx->ready_vals[c] = (int32_t)std::min(n_order, (c + 1) * ctx->seed_chunk);
+        CK(cudaMemcpyAsync(ctx->d_seed_ready, &ctx->ready_vals[c], sizeof(int32_t), cudaMemcpyHostToDevice, ctx->pub));
+    }
     if (ctx->seeder.joinable()) ctx->seeder.join();
     ctx->seed_pending = false;
-    if (ctx->anc.size() > ctx->b_anc.cap / sizeof(int32_t)) { ctx->err = "anchor buffer too small"; return MPOA_EINVAL; }
-    CK(cudaMemcpyAsync(ctx->d_anc_off, ctx->anc_off.data(), ctx->anc_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    if (!ctx->anc.empty()) CK(cudaMemcpyAsync(ctx->d_anc, ctx->anc.data(), ctx->anc.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(ctx->pub));
+    ctx->seed_wait_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return MPOA_OK;
 }
 
@@ -662,7 +789,8 @@ static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_la
     if (n_big == 0) live[0]->small = false;           // nothing to run beside
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
-    const uint64_t budget = (uint64_t)(((uint64_t)free_b + ctx->ws_bytes) * 0.85);
+    DevShared &D = g_dev[ctx->dev];                   // (the caller holds D.mu)
+    const uint64_t budget = (uint64_t)(((uint64_t)free_b + D.ws_bytes) * 0.85);
     /* the big launches share one workspace (they run one after the other), every small one has its own */
     uint64_t need_big = 0, need_small = 0;
     for (Launch *ln : live) {
@@ -689,11 +817,11 @@ static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_la
         need_small = 0;
     }
     const uint64_t need = need_big + need_small;
-    if (need > ctx->ws_bytes) {
-        cudaFree(ctx->d_ws);
-        ctx->d_ws = nullptr; ctx->ws_bytes = 0;
-        CK(cudaMalloc(&ctx->d_ws, need));
-        ctx->ws_bytes = need;
+    if (need > D.ws_bytes) {
+        cudaFree(D.ws);
+        D.ws = nullptr; D.ws_bytes = 0;
+        CK(cudaMalloc(&D.ws, need));
+        D.ws_bytes = need;
     }
     size_t q_off = 0;
     std::vector<int32_t> hq;
@@ -740,7 +868,6 @@ static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_la
             used_side2 = true;
         }
         if (!ln->small) first_big = false;
-        if (ln->seeded) { const int rc = finish_seeding(ctx, st); if (rc != MPOA_OK) return rc; }
         CK(launch_poa(ln->c.code(), A, (int)ln->n_blocks, ln->wpb, st));
         ++*n_launch;
         if (verbose)
@@ -756,7 +883,7 @@ static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_la
         CK(cudaEventRecord(ctx->join2_ev, ctx->side2));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->join2_ev, 0));
     }
-    return MPOA_OK;
+    return publish_seeds(ctx);                        // (first round only) feeds the seeded launches while they run
 }
 
 extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
@@ -771,23 +898,13 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
     if (ng == 0) { ctx->ran = true; ctx->last = st; if (stats) *stats = st; return MPOA_OK; }
     CK(cudaMemsetAsync(ctx->d_stats, 0, SI_COUNT * sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_cons_len, 0, ng * sizeof(int32_t), ctx->stream));
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    /* kernel phase: one context per device at a time (DevShared); taken in front of the first launch */
+    std::unique_lock<std::mutex> kernel_phase(g_dev[ctx->dev].mu, std::defer_lock);
 
     std::vector<int32_t> pending(ng);
     std::iota(pending.begin(), pending.end(), 0);
-    /* tuning aid: bit l set = packed level l may be scheduled (default: all) */
-    unsigned level_mask = ~0u;
-    if (const char *ml = getenv("MPOA_LEVELS")) level_mask = (unsigned)strtoul(ml, nullptr, 0) | ~0x7u;
-    auto pick_level = [&](const GroupInfo &gi, int wneed) {
-        for (int l = 0; l < kNumLevels; ++l) {
-            if (!((level_mask >> l) & 1u)) continue;
-            if (kLevels[l].WPL != 0 && !gi.lanes16) continue;
-            /* a lane wider than abPOA's vector length may start up to (2*WPL - pn) cells before the band */
-            const int slack = std::max(0, 2 * kLevels[l].WPL - ctx->params.simd_pn_i32);
-            if (kLevels[l].wcap >= wneed + slack) return l;
-        }
-        return kNumLevels - 1;
-    };
+    const unsigned level_mask = level_mask_env();
+    auto pick_level = [&](const GroupInfo &gi, int wneed) { return ::pick_level(ctx->params, level_mask, gi.lanes16 != 0, wneed); };
     for (int64_t g = 0; g < ng; ++g) {
         GroupInfo &gi = ctx->ginfo[g];
         gi.lanes16 = 1;
@@ -866,11 +983,26 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
             launches.back().c = c;
         }
         {
+            if (!kernel_phase.owns_lock()) {
+                const auto tw = std::chrono::steady_clock::now();
+                kernel_phase.lock();
+                st.kernel_wait_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw).count();
+                CK(cudaEventRecord(ctx->ev0, ctx->stream));
+                if (ctx->need_encode) {
+                    CK(launch_encode(ctx->d_ascii, ctx->d_codes, ctx->n_bases, ctx->stream));
+                    ctx->need_encode = false;
+                    ++n_launch;
+                }
+            }
             const int rc = run_round(ctx, launches, &n_launch);
             if (rc < 0) return rc;
         }
+        /* wait FIRST: a copy into pageable memory keeps its caller inside the driver until the stream gets to
+         * it -- here: behind the kernels -- and other host threads' CUDA calls (another context uploading its
+         * batch beside these kernels) were measured to wait with it */
         CK(cudaStreamSynchronize(ctx->stream));
-        CK(cudaMemcpy(dstat.data(), ctx->d_status, ng * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpyAsync(dstat.data(), ctx->d_status, ng * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
         std::vector<int32_t> next;
         for (int32_t g : pending) {
             if (ctx->h_status[g] == ST_EMPTY || ctx->h_status[g] == ST_TOO_BIG) continue;  // not launchable
@@ -897,13 +1029,33 @@ extern "C" int mpoa_batch_run(mpoa_ctx *ctx, mpoa_stats *stats) {
         pending.swap(next);
     }
     for (int32_t g : pending) ctx->h_status[g] = ST_TOO_BIG;  // still too big after the last attempt
-    { const int rc = finish_seeding(ctx, ctx->stream); if (rc != MPOA_OK) return rc; }   // no seeded launch was made
+    { const int rc = publish_seeds(ctx); if (rc != MPOA_OK) return rc; }   // no launch was made at all
+    if (!kernel_phase.owns_lock()) { kernel_phase.lock(); CK(cudaEventRecord(ctx->ev0, ctx->stream)); }
+    /* still inside the kernel phase: the consensi are gathered into one compact buffer, so that mpoa_batch_fetch
+     * is copies only (it may run while the next batch's kernels hold the SMs) */
+    {
+        std::vector<int32_t> len(ng);
+        CK(cudaMemcpyAsync(len.data(), ctx->d_cons_len, ng * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->h_cons_off.assign(ng + 1, 0);
+        for (int64_t g = 0; g < ng; ++g) ctx->h_cons_off[g + 1] = ctx->h_cons_off[g] + (ctx->h_status[g] == ST_OK ? len[g] : 0);
+        const int64_t total = ctx->h_cons_off[ng];
+        if (total > 0) {
+            CK(ctx->b_out_off.ensure((ng + 1) * sizeof(int64_t)));
+            CK(ctx->b_out.ensure(total));
+            CK(cudaMemcpyAsync(ctx->b_out_off.p, ctx->h_cons_off.data(), (ng + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+            CK(launch_gather(ctx->d_cons, ctx->d_region_off, (int64_t *)ctx->b_out_off.p, (uint8_t *)ctx->b_out.p, ng, ctx->stream));
+            ++n_launch;
+        }
+    }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    kernel_phase.unlock();
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     unsigned long long hs[SI_COUNT];
-    CK(cudaMemcpy(hs, ctx->d_stats, sizeof(hs), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(hs, ctx->d_stats, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     st.kernel_ms = ms;
     st.band_cells = (int64_t)hs[SI_CELLS]; st.int_ops = (int64_t)hs[SI_INTOPS]; st.full_cells = (int64_t)hs[SI_FULL];
     st.n_alignments = (int64_t)hs[SI_ALN]; st.n_align_i16 = (int64_t)hs[SI_ALN16]; st.n_align_i32 = (int64_t)hs[SI_ALN32];
@@ -930,35 +1082,22 @@ extern "C" int mpoa_batch_fetch(mpoa_ctx *ctx, int64_t *cons_off, uint8_t *cons_
     cons_off[0] = 0;
     if (ng == 0) return MPOA_OK;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    std::vector<int32_t> len(ng);
-    CK(cudaMemcpyAsync(len.data(), ctx->d_cons_len, ng * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
     for (int64_t g = 0; g < ng; ++g) {
         const bool ok = ctx->h_status[g] == ST_OK;
-        cons_off[g + 1] = cons_off[g] + (ok ? len[g] : 0);
+        cons_off[g + 1] = ctx->h_cons_off[g + 1];
         if (group_status) group_status[g] = ok ? MPOA_GROUP_OK : ctx->h_status[g] == ST_TOO_BIG ? MPOA_GROUP_TOO_BIG : MPOA_GROUP_EMPTY;
     }
     const int64_t total = cons_off[ng];
     int rc = MPOA_OK;
     if (total > cons_cap || (total > 0 && !cons_buf)) rc = MPOA_ENOSPC;
-    else if (total > 0) {
-        CK(ctx->b_out_off.ensure((ng + 1) * sizeof(int64_t)));
-        CK(ctx->b_out.ensure(total));
-        int64_t *d_out_off = (int64_t *)ctx->b_out_off.p;
-        uint8_t *d_out = (uint8_t *)ctx->b_out.p;
-        CK(cudaMemcpyAsync(d_out_off, cons_off, (ng + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-        CK(launch_gather(ctx->d_cons, ctx->d_region_off, d_out_off, d_out, ng, ctx->stream));
-        CK(cudaMemcpyAsync(cons_buf, d_out, total, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        ctx->last.n_kernel_launches += 1;
-    }
+    else if (total > 0) CK(cudaMemcpyAsync(cons_buf, ctx->b_out.p, total, cudaMemcpyDeviceToHost, ctx->stream));
     if (trace && ctx->want_trace) {
         const int64_t nr = ctx->n_reads, nb = ctx->n_bases;
-        if (trace->read_score) CK(cudaMemcpy(trace->read_score, ctx->d_tr_score, nr * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        if (trace->read_bits) CK(cudaMemcpy(trace->read_bits, ctx->d_tr_bits, nr * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        if (trace->read_band_cells) CK(cudaMemcpy(trace->read_band_cells, ctx->d_tr_cells, nr * sizeof(long long), cudaMemcpyDeviceToHost));
-        if (trace->base_aln) CK(cudaMemcpy(trace->base_aln, ctx->d_tr_aln, nb * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        if (trace->base_node) CK(cudaMemcpy(trace->base_node, ctx->d_tr_node, nb * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (trace->read_score) CK(cudaMemcpyAsync(trace->read_score, ctx->d_tr_score, nr * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (trace->read_bits) CK(cudaMemcpyAsync(trace->read_bits, ctx->d_tr_bits, nr * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (trace->read_band_cells) CK(cudaMemcpyAsync(trace->read_band_cells, ctx->d_tr_cells, nr * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        if (trace->base_aln) CK(cudaMemcpyAsync(trace->base_aln, ctx->d_tr_aln, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (trace->base_node) CK(cudaMemcpyAsync(trace->base_node, ctx->d_tr_node, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

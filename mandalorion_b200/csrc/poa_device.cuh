@@ -86,9 +86,14 @@ struct KernelArgs {
     int32_t *tr_score, *tr_bits;     // optional trace (NULL when off)
     long long *tr_cells;
     int32_t *tr_aln, *tr_node;
-    /* `abpoa -S` launches: anchors (start in the previous read, start in this read) of every read */
-    const int32_t *anc_off;          // [n_reads+1]
+    /* `abpoa -S` launches: read r owns the slots anc[anc_off[r] ...]: (number of anchors, 0), then the anchors
+     * (start in the previous read, start in this read).  The host may still be computing anchors when the launch
+     * starts: group g may be started once *seed_ready > seed_rank[g] (seed_ready == NULL: everything is there);
+     * the host copies a chunk of anchors and then the counter on one stream, the kernel reads both past L1. */
+    const int32_t *anc_off;          // [n_reads]
     const int2 *anc;
+    const int32_t *seed_rank;        // [n_groups]
+    const int32_t *seed_ready;
     int seed_k;
     DevParams P;
     Packed16 K;

@@ -152,7 +152,7 @@ __device__ __forceinline__ int read_step(const KernelArgs &A, const Team<T> &tm,
         const int k = A.seed_k;
         const int32_t *prevrow = prevrow_p(A, S);
         int32_t *qmap = qmap_p(A, S);
-        const int a0 = aln ? A.anc_off[r] : 0, n_anc = aln ? A.anc_off[r + 1] - a0 : -1;
+        const int a0 = aln ? A.anc_off[r] + 1 : 0, n_anc = aln ? __ldcg(A.anc + (a0 - 1)).x : -1;
         const int n_win = tm.wmax(n_anc + 1);
         Slot V = S;
         V.sub = 1;
@@ -162,7 +162,7 @@ __device__ __forceinline__ int read_step(const KernelArgs &A, const Team<T> &tm,
         for (int wi = 0; wi < n_win; ++wi) {
             const bool won = aln && wi <= n_anc;
             int re = G.N - 1, qend = len, t0 = 0;
-            if (won && wi < n_anc) { const int2 an = A.anc[a0 + wi]; t0 = an.x; qend = an.y; re = prevrow[t0]; }
+            if (won && wi < n_anc) { const int2 an = __ldcg(A.anc + (a0 + wi)); t0 = an.x; qend = an.y; re = prevrow[t0]; }
             const int ql = qend - qbeg;
             bool run = won && ql > 0;
             if (tm.wany(run)) {
@@ -296,12 +296,34 @@ poa_group_kernel(const __grid_constant__ KernelArgs A) {
     GroupState G;
     G.g = -1; G.r = G.r1 = 0; G.gbase = 0; G.N = G.E = G.par = 0; G.t0 = 0;
     bool dry = false;        // the queue has nothing left for this team
+    bool gave_up = false;    // (seeded launches) the host stopped publishing anchors
     for (;;) {
         if (G.g < 0 && !dry) {                        // per team; team lane 0 only, no cross-lane operation
             int g = -1;
             if (tm.tl == 0) {
-                const int qi = atomicAdd(A.queue_head, 1);
-                if (qi < A.n_queue) g = A.queue[qi];
+                for (;;) {
+                    const int qi = atomicAdd(A.queue_head, 1);
+                    g = qi < A.n_queue ? A.queue[qi] : -1;
+                    if constexpr (SEEDED) {
+                        /* the anchors of this group may still be on their way (poa_capi.cu: publish_seeds).  The wait
+                         * is bounded: a group whose anchors do not arrive goes back to the host, which runs it again */
+                        if (g >= 0 && A.seed_ready != nullptr) {
+                            const int need = A.seed_rank[g];
+                            const volatile int32_t *rdy = A.seed_ready;
+                            unsigned long long t_start = 0;
+                            while (!gave_up && *rdy <= need) {
+                                unsigned long long now;
+                                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                                if (t_start == 0) t_start = now;
+                                if (now - t_start > 30000000000ull) gave_up = true;     // 30 s
+                                else __nanosleep(20000);
+                            }
+                            if (*rdy <= need) { A.status[g] = ST_RETRY | (A.level << 8); A.cons_len[g] = 0; continue; }
+                            __threadfence();
+                        }
+                    }
+                    break;
+                }
                 if (g >= 0) {
 #pragma unroll
                     for (int k = 0; k < SI_COUNT; ++k) gst[k] = 0;

@@ -38,16 +38,26 @@ inline uint64_t hash_kmer(uint64_t x, uint64_t mask) {
     return x;
 }
 
-inline int code_of(uint8_t c) {
-    switch (c & 0xdf) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; default: return 4; }
-}
+struct CodeTable {
+    uint8_t v[256];
+    CodeTable() {
+        for (int c = 0; c < 256; ++c) {
+            switch (c & 0xdf) { case 'A': v[c] = 0; break; case 'C': v[c] = 1; break; case 'G': v[c] = 2; break; case 'T': v[c] = 3; break; default: v[c] = 4; }
+        }
+    }
+};
+const CodeTable kCodes;
+inline int code_of(uint8_t c) { return kCodes.v[c]; }
 
 /* forward-strand (w,k) minimizers of an ASCII read */
 void forward_minimizers(const uint8_t *s, int n, int w, int k, std::vector<KmerAt> &out) {
     out.clear();
     const uint64_t mask = (1ULL << (2 * k)) - 1;
-    std::vector<uint64_t> ring_h(w, UINT64_MAX);
-    std::vector<int32_t> ring_end(w, 0);
+    uint64_t ring_h[256];
+    int32_t ring_end[256];
+    if (w > 256) w = 256;
+    for (int j = 0; j < w; ++j) { ring_h[j] = UINT64_MAX; ring_end[j] = 0; }
+    out.reserve((size_t)n / 4 + 16);
     uint64_t word = 0, cur_min = UINT64_MAX;
     int32_t cur_end = 0;
     int run = 0, slot = 0, min_slot = 0;
@@ -69,10 +79,10 @@ void forward_minimizers(const uint8_t *s, int n, int w, int k, std::vector<KmerA
             if (run >= w + k - 1) put(cur_min, cur_end);
             uint64_t best = UINT64_MAX;
             int where = slot;
-            for (int t = 1; t <= w; ++t) {
-                const int j = (slot + t) % w;
+            for (int j = slot + 1; j < w; ++j)          // oldest to newest: slot+1 .. w-1, then 0 .. slot
                 if (ring_h[j] <= best) { best = ring_h[j]; where = j; }
-            }
+            for (int j = 0; j <= slot; ++j)
+                if (ring_h[j] <= best) { best = ring_h[j]; where = j; }
             cur_min = best; cur_end = ring_end[where]; min_slot = where;
             if (run >= w + k - 1 && cur_min != UINT64_MAX) { put_equal(slot + 1, w); put_equal(0, slot + 1); }
         }
@@ -141,7 +151,7 @@ struct KmerTable {
 
 void anchors_of(const KmerTable &prev, const std::vector<KmerAt> &cur, int k, int min_gap,
                 std::vector<Pair> &hits, std::vector<int32_t> &score, std::vector<int32_t> &from, std::vector<int32_t> &ht,
-                std::vector<int32_t> &hq, std::vector<int32_t> &out) {
+                std::vector<int32_t> &hq, int32_t *out, int cap, int32_t *n_out) {
     hits.clear();
     for (const KmerAt &m : cur) {
         const KmerTable::Slot *x = prev.find(m.h);
@@ -167,7 +177,9 @@ void anchors_of(const KmerTable &prev, const std::vector<KmerAt> &cur, int k, in
     for (auto it = path.rbegin(); it != path.rend(); ++it) {
         const int32_t t0 = hits[*it].t - k + 1, q0 = hits[*it].q - k + 1;
         if (t0 - (end_t + 1) >= min_gap && q0 - (end_q + 1) >= min_gap) {
-            out.push_back(t0); out.push_back(q0);
+            if (*n_out >= cap) break;                  // cannot happen: anchors are >= min_gap apart (cap = len / min_gap + 1)
+            out[2 * *n_out] = t0; out[2 * *n_out + 1] = q0;
+            ++*n_out;
             end_t = hits[*it].t; end_q = hits[*it].q;
         }
     }
@@ -176,16 +188,17 @@ void anchors_of(const KmerTable &prev, const std::vector<KmerAt> &cur, int k, in
 }  // namespace
 
 /*
- * Anchors of every read of the flagged groups: anc_off[n_reads + 1] (prefix counts of anchors),
- * anc = (start in the previous read, start in this read) pairs.  Unflagged groups and first reads
- * have none.  n_threads host threads over groups.  src_off (nullable): where read r starts in
+ * Anchors of the reads of the groups order[0..n_order) (the flagged groups, in the order the device will ask
+ * for them).  Read r owns the slots anc[2 * anc_off[r] ...] of the arena: slot 0 = (number of anchors, 0),
+ * then up to len / min_gap + 1 (start in the previous read, start in this read) pairs -- anchors are at least
+ * min_gap apart, so the regions can be laid out before the anchors exist.  n_threads host threads take the
+ * groups in order; done[i / chunk_size] counts the finished groups of every chunk, so that the consumer can
+ * publish chunk 0 while the later ones are still being computed.  src_off (nullable): where read r starts in
  * `bases` when the batch is a subset of the caller's arrays (default: rbo[r]).
  */
-void seed_batch(int64_t n_groups, const int64_t *gro, const int64_t *rbo, const uint8_t *bases, const int64_t *src_off,
-                const uint8_t *flags, int k, int w, int min_gap, int n_threads, std::vector<int32_t> &anc_off,
-                std::vector<int32_t> &anc) {
-    const int64_t n_reads = n_groups > 0 ? gro[n_groups] : 0;
-    std::vector<std::vector<int32_t>> per_read((size_t)n_reads);
+void seed_batch(const int64_t *gro, const int64_t *rbo, const uint8_t *bases, const int64_t *src_off,
+                const int32_t *order, int64_t n_order, int64_t chunk_size, std::atomic<int64_t> *done,
+                int k, int w, int min_gap, int n_threads, const int32_t *anc_off, int32_t *anc) {
     std::atomic<int64_t> next(0);
     auto worker = [&]() {
         std::vector<KmerAt> cur;
@@ -193,33 +206,31 @@ void seed_batch(int64_t n_groups, const int64_t *gro, const int64_t *rbo, const 
         std::vector<Pair> hits;
         std::vector<int32_t> score, from, ht, hq;
         for (;;) {
-            const int64_t g = next.fetch_add(1);
-            if (g >= n_groups) break;
-            if (!flags || !(flags[g] & 1)) continue;
+            const int64_t i = next.fetch_add(1);
+            if (i >= n_order) break;
+            const int64_t g = order[i];
             int64_t prev_r = -1;
             for (int64_t r = gro[g]; r < gro[g + 1]; ++r) {
                 const int len = (int)(rbo[r + 1] - rbo[r]);
+                int32_t *region = anc + 2 * (int64_t)anc_off[r];
+                region[0] = 0; region[1] = 0;
                 if (len <= 0) continue;                 // an empty read is skipped by the aligner too
                 forward_minimizers(bases + (src_off ? src_off[r] : rbo[r]), len, w, k, cur);
-                if (prev_r >= 0) anchors_of(prev, cur, k, min_gap, hits, score, from, ht, hq, per_read[(size_t)r]);
+                if (prev_r >= 0)
+                    anchors_of(prev, cur, k, min_gap, hits, score, from, ht, hq, region + 2, len / min_gap + 1, region);
                 prev.build(cur);
                 prev_r = r;
             }
+            if (done) done[chunk_size > 0 ? i / chunk_size : 0].fetch_add(1, std::memory_order_release);
         }
     };
     int nt = std::max(1, n_threads);
-    if ((int64_t)nt > n_groups) nt = (int)std::max<int64_t>(1, n_groups);
+    if ((int64_t)nt > n_order) nt = (int)std::max<int64_t>(1, n_order);
     if (nt <= 1) worker();
     else {
         std::vector<std::thread> th;
         for (int t = 0; t < nt; ++t) th.emplace_back(worker);
         for (auto &t : th) t.join();
-    }
-    anc_off.assign((size_t)n_reads + 1, 0);
-    anc.clear();
-    for (int64_t r = 0; r < n_reads; ++r) {
-        anc.insert(anc.end(), per_read[(size_t)r].begin(), per_read[(size_t)r].end());
-        anc_off[(size_t)r + 1] = (int32_t)(anc.size() / 2);
     }
 }
 

@@ -37,7 +37,8 @@ class _Stats(C.Structure):
                 ("n_retry_groups", C.c_int64), ("kernel_ms", C.c_double), ("h2d_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("n_kernel_launches", C.c_int64), ("phase_cycles", C.c_int64 * 6),
                 ("n_seed_groups", C.c_int64), ("n_seed_applied", C.c_int64), ("n_too_big_groups", C.c_int64),
-                ("max_band_width", C.c_int64), ("host_seed_ms", C.c_double), ("reserved", C.c_int64 * 3)]
+                ("max_band_width", C.c_int64), ("host_seed_ms", C.c_double), ("kernel_wait_ms", C.c_double),
+                ("reserved", C.c_int64 * 2)]
 
 
 class _Trace(C.Structure):
@@ -327,3 +328,77 @@ class PoaContext:
         self.last_stats = self._stats_dict(st)
         return dict(cons=_split(cons_buf[:cons_off[ng]].tobytes(), cons_off), status=status, cons_off=cons_off,
                     trace=arrs, stats=self.last_stats)
+
+
+class PoaPipeline:
+    """Batches in flight on ONE GPU: `depth` contexts, each served by its own host thread, so that the
+    host->device copy, the host-side passes and the result split of one batch run while the kernels of
+    another occupy the SMs, and the persistent blocks of the next batch move in while the last groups of
+    the previous one drain.  This is how a streaming caller (dstep.StreamingConsensus: loci arriving one
+    after the other, reference defineIsoforms.py:130-153) keeps the GPU busy.  Every context owns a
+    non-blocking stream (mpoa_create), so the contexts only meet in the hardware's block scheduler.
+
+        with PoaPipeline(device=0, depth=2) as pipe:
+            futures = [pipe.submit(packed=p, flags=f) for p, f in batches]
+            results = [f.result() for f in futures]        # dicts as from PoaContext.consensus_batch
+
+    Results are identical to PoaContext.consensus_batch on the same batch (groups are independent)."""
+
+    def __init__(self, device=0, depth=2, params=None, contexts=None):
+        import queue
+        import threading
+        self._own = contexts is None
+        self.contexts = list(contexts) if contexts is not None else [PoaContext(device, params) for _ in range(depth)]
+        if not self.contexts:
+            raise PoaError("PoaPipeline needs at least one context")
+        self._jobs = queue.Queue()
+        self._threads = [threading.Thread(target=self._serve, args=(c,), daemon=True) for c in self.contexts]
+        for t in self._threads:
+            t.start()
+
+    def _serve(self, ctx):
+        while True:
+            job = self._jobs.get()
+            if job is None:
+                return
+            fut, kw = job
+            if not fut.set_running_or_notify_cancel():
+                continue
+            try:
+                import time
+                t0 = time.perf_counter()
+                res = ctx.consensus_batch(**kw)
+                res["wall"] = (t0, time.perf_counter())      # when this batch was in its context (perf_counter)
+                fut.set_result(res)
+            except BaseException as e:       # noqa: BLE001 -- handed to the caller through the future
+                fut.set_exception(e)
+
+    def submit(self, groups=None, packed=None, trace=False, flags=None):
+        """Queues one batch; returns a concurrent.futures.Future of PoaContext.consensus_batch's dict.  The
+        caller's arrays must stay unchanged until the future is done."""
+        from concurrent.futures import Future
+        fut = Future()
+        self._jobs.put((fut, dict(groups=groups, packed=packed, trace=trace, flags=flags)))
+        return fut
+
+    def map(self, batches):
+        """batches: iterable of (packed, flags); yields the results in input order."""
+        futs = [self.submit(packed=p, flags=f) for p, f in batches]
+        for f in futs:
+            yield f.result()
+
+    def close(self):
+        for _ in self._threads:
+            self._jobs.put(None)
+        for t in self._threads:
+            t.join()
+        self._threads = []
+        if self._own:
+            for c in self.contexts:
+                c.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

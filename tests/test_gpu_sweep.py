@@ -100,3 +100,41 @@ def test_seeded_long_reads_with_structural_differences(gpu_ctx):
     want = oracle_consensus_batch(packed=packed, trace=True, n_threads=THREADS, flags=flags)
     got = gpu_ctx.consensus_batch(packed=packed, trace=True, flags=flags)
     assert_same(got, want, packed)
+
+
+def test_seeded_three_stage_interface_and_many_chunks(gpu_ctx):
+    """upload / run / fetch seed inside the upload (the caller's buffer is free when upload returns); the
+    one-call entry seeds beside the kernels and publishes the anchors chunk by chunk (poa_capi.cu:
+    publish_seeds) -- more groups than one chunk holds, so that launches really wait for later chunks.  Both
+    must give the seeded oracle's answer."""
+    n = 40
+    groups = make_groups("cfg1", n, first=900)
+    packed = pack_groups(groups)
+    flags = (np.arange(n) % 5 != 0).astype(np.uint8)
+    want = oracle_consensus_batch(packed=packed, n_threads=THREADS, flags=flags)
+    one_call = gpu_ctx.consensus_batch(packed=packed, flags=flags)
+    assert_same(one_call, want, packed, check_trace=False)
+    gpu_ctx.upload(*packed, flags=flags)
+    for _ in range(2):                                   # the anchors stay resident between runs
+        st = gpu_ctx.run()
+        got = gpu_ctx.fetch()
+        got["stats"] = st
+        assert_same(got, want, packed, check_trace=False)
+
+
+def test_pipeline_of_contexts_gives_the_same_answers(built):
+    """PoaPipeline: several batches in flight on one GPU (two contexts, each on its own stream and host
+    thread).  Every batch must come back exactly as a lone PoaContext.consensus_batch() returns it."""
+    from mandalorion_b200 import PoaPipeline
+    batches = []
+    for i, (cfg, n) in enumerate((("cfg1", 64), ("cfg2", 24), ("cfg3", 6), ("cfg1", 80), ("cfg4", 3), ("cfg2", 16))):
+        packed = pack_groups(make_groups(cfg, n, first=100 * i))
+        flags = (np.arange(n) % 2 == (i % 2)).astype(np.uint8) if cfg == "cfg3" else None
+        batches.append((packed, flags))
+    with PoaPipeline(device=0, depth=2) as pipe:
+        futs = [pipe.submit(packed=p, flags=f) for p, f in batches]
+        got = [f.result() for f in futs]
+        again = list(pipe.map(batches[:2]))
+    for (packed, flags), g in zip(batches + batches[:2], got + again):
+        want = oracle_consensus_batch(packed=packed, n_threads=THREADS, flags=flags)
+        assert_same(g, want, packed, check_trace=False)
