@@ -14,7 +14,10 @@
  *
  * Conventions: plain pointers and sizes; every buffer is caller-owned; return value
  * 0 = ok, negative = MPOA_E*; no exceptions cross the ABI; a context is bound to one
- * CUDA device and is not thread-safe (one context per host thread / GPU).
+ * CUDA device and is not thread-safe (one context per host thread).  Several contexts may
+ * live on one GPU: their kernels take turns (mpoa_batch_run holds a per-device lock while
+ * its kernels run) and share one workspace; uploads and fetches are copies only and run
+ * beside another context's kernels.
  * There is no CPU path behind this ABI: mpoa_create() fails when no CUDA device is
  * usable.
  */

@@ -204,11 +204,10 @@ class ConsensusBatcher:
             chunk = todo[start:end]
             gro, rbo, bases = pack_groups([pg.sequences for pg in chunk])
             flags = np.array([1 if pg.seed else 0 for pg in chunk], dtype=np.uint8)
-            ctx = self.ctx
-            ctx.upload(gro, rbo, bases, flags)
-            st = ctx.run()
+            # ONE C call: the `-S` anchors are computed beside the kernels (mpoa_consensus_batch)
+            out = self.ctx.consensus_batch(packed=(gro, rbo, bases), flags=flags)
+            st = out["stats"]
             self.stats.append(st)
-            out = ctx.fetch()
             n_unseeded = st.get("n_seed_groups", 0) - st.get("n_seed_applied", 0)
             if n_unseeded > 0:
                 warnings.warn(f"{n_unseeded} group(s) with median read length >= 8000: the reference runs `abpoa -S` "

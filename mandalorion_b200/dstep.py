@@ -56,10 +56,14 @@ def iter_psl(path):
 
 
 class StreamingConsensus:
-    """See the module docstring.  batch_bases: a batch is issued once this many read bases are pending."""
+    """See the module docstring.  batch_bases: a batch is issued once this many read bases are pending.
+    depth: batches in flight -- every one has its own context and host thread, so that the orientation, the
+    host->device copy and the result split of one batch run beside the kernels of another (the library lets
+    the contexts of one GPU take turns on the SMs and share one workspace: poa.PoaPipeline).
+    With an explicit `ctx` the first batch slot uses it."""
 
-    def __init__(self, ctx=None, device=0, batch_bases=256 << 20, orient_threads=None):
-        self._batcher = ConsensusBatcher(ctx, device=device)
+    def __init__(self, ctx=None, device=0, batch_bases=256 << 20, orient_threads=None, depth=1):
+        self._batchers = [ConsensusBatcher(ctx if k == 0 else None, device=device) for k in range(max(1, depth))]
         self._batch_bases = batch_bases
         self._orient_threads = orient_threads
         self._order = []                      # (root, {isoform: PendingGroup}) in insertion order
@@ -67,10 +71,12 @@ class StreamingConsensus:
         self._q = queue.Queue(maxsize=4)
         self._err = None
         self.n_batches = 0
-        self._worker = threading.Thread(target=self._run, daemon=True)
-        self._worker.start()
+        self._lock = threading.Lock()
+        self._workers = [threading.Thread(target=self._run, args=(b,), daemon=True) for b in self._batchers]
+        for w in self._workers:
+            w.start()
 
-    def _run(self):
+    def _run(self, batcher):
         while True:
             chunk = self._q.get()
             if chunk is None:
@@ -79,9 +85,10 @@ class StreamingConsensus:
                 if self._err is None:
                     orient_pending(chunk, n_threads=self._orient_threads)
                     for pg in chunk:
-                        self._batcher.add(pg)
-                    self._batcher.flush()
-                    self.n_batches += 1
+                        batcher.add(pg)
+                    batcher.flush()
+                    with self._lock:
+                        self.n_batches += 1
             except Exception as e:            # surfaced by add_locus() / finish()
                 self._err = e
 
@@ -105,15 +112,17 @@ class StreamingConsensus:
     def finish(self):
         """Runs what is still pending and returns {root: {isoform: [consensus, names]}} in insertion order."""
         self._issue()
-        self._q.put(None)
-        self._worker.join()
+        for _ in self._workers:
+            self._q.put(None)
+        for w in self._workers:
+            w.join()
         if self._err is not None:
             raise self._err
         return {root: {isoform: [pg.consensus, pg.names] for isoform, pg in iso.items()} for root, iso in self._order}
 
     @property
     def stats(self):
-        return self._batcher.stats
+        return [st for b in self._batchers for st in b.stats]
 
 
 def locus_roots(tmp_ss):
@@ -133,7 +142,8 @@ def _produce(job):
 
 def define_isoforms(out_path, ctx=None, device=0, left_bounds=None, right_bounds=None, splice_site_width=1,
                     minimum_read_count=2, junctions=("gtag", "gcag", "atac", "ctac", "ctgc", "gtat"), cutoff=0.1,
-                    upstream_buffer=10, downstream_buffer=50, batch_bases=256 << 20, orient_threads=None, workers=0):
+                    upstream_buffer=10, downstream_buffer=50, batch_bases=256 << 20, orient_threads=None, workers=0,
+                    depth=2):
     """Module D (`defineIsoforms.py -p out_path ...`, reference defineIsoforms.py:93-168) on one GPU:
     reads out_path/tmp_SS/*.psl, writes out_path/Isoform_Consensi.fasta and reads2isoforms.txt.
 
@@ -145,13 +155,14 @@ def define_isoforms(out_path, ctx=None, device=0, left_bounds=None, right_bounds
     NumPy RNG state; the same is done here (state saved at entry, restored before every locus), which makes
     the output identical to a reference run started from the same state.  workers > 0: the loci are parsed
     and grouped by that many producer processes (spawned, so that no CUDA state is forked), consumed in locus
-    order while the GPU works on earlier loci; the result does not depend on it.  Returns the number of isoforms."""
+    order while the GPU works on earlier loci; the result does not depend on it.  depth: GPU batches in flight
+    (StreamingConsensus).  Returns the number of isoforms."""
     import time
     tmp_ss = os.path.join(out_path, "tmp_SS")
     roots = locus_roots(tmp_ss)
     junctions = list(junctions)
     entry_state = np.random.get_state()
-    sc = StreamingConsensus(ctx, device=device, batch_bases=batch_bases, orient_threads=orient_threads)
+    sc = StreamingConsensus(ctx, device=device, batch_bases=batch_bases, orient_threads=orient_threads, depth=depth)
     t = dict(producer=0.0, prepare=0.0, drain=0.0, write=0.0)
     n_reads = 0
     par = (splice_site_width, minimum_read_count, junctions, cutoff, upstream_buffer, downstream_buffer)
