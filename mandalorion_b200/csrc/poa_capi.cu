@@ -764,6 +764,7 @@ static int run_round(mpoa_ctx *ctx, std::vector<Launch> &launches, int64_t *n_la
     std::vector<Launch *> live;
     for (Launch &ln : launches) {
         ln.wpb = 4;
+        if (const char *w = getenv("MPOA_WPB")) ln.wpb = std::max(1, std::min(4, atoi(w)));   // tuning aid: warps per block
         while (ln.wpb > 1 && poa_smem_bytes(ln.c.code(), ln.c.wcap, ln.wpb) > ctx->smem_optin) ln.wpb >>= 1;
         ln.bps = poa_smem_bytes(ln.c.code(), ln.c.wcap, ln.wpb) > ctx->smem_optin
                      ? 0 : poa_max_blocks_per_sm(ln.c.code(), ln.c.wcap, ln.wpb, ln.seeded);

@@ -182,8 +182,10 @@ def test_dstep_with_native_orientation_on_the_gpu(gpu_ctx, tmp_path, monkeypatch
         assert results["chr1~%d~%d" % (g * 1000, g * 1000 + 900)]["1"][0] == want
 
 
-def test_streaming_dispatch_on_the_gpu(gpu_ctx, monkeypatch):
-    """loci fed one by one, GPU batches issued in the background: same IsoData as the collect-everything path"""
+@pytest.mark.parametrize("depth", [1, 2])
+def test_streaming_dispatch_on_the_gpu(gpu_ctx, monkeypatch, depth):
+    """loci fed one by one, GPU batches issued in the background (depth 2: two batches in flight, two contexts):
+    same IsoData as the collect-everything path"""
     from mandalorion_b200 import dstep
     monkeypatch.setattr(cons_mod, "mappy_available", lambda: False)
     groups = make_groups("cfg1", 48, random_strand=True, with_names=True)
@@ -193,7 +195,7 @@ def test_streaming_dispatch_on_the_gpu(gpu_ctx, monkeypatch):
         return {"chr2~%d~%d" % (g * 1000, g * 1000 + 900): {"1": cons_mod.prepare_group(reads)} for g, reads in enumerate(groups)}
 
     want = cons_mod.finish_prepared(prepared(), ctx=gpu_ctx)
-    sc = dstep.StreamingConsensus(gpu_ctx, batch_bases=150000)
+    sc = dstep.StreamingConsensus(gpu_ctx, batch_bases=150000, depth=depth)
     for root, iso in prepared().items():
         sc.add_locus(root, iso)
     got = sc.finish()
