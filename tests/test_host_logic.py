@@ -142,3 +142,32 @@ def test_abpoa_cli_argument_protocol(tmp_path):
     assert abpoa_cli.read_fasta(str(fa)) == ["ACGTAC", "GGTT"]
     with pytest.raises(SystemExit):
         abpoa_cli.parse_args(["-r", "1", "x.fasta"])
+
+
+def test_pipeline_host_logic_without_a_gpu():
+    """PoaPipeline is host logic over objects with a consensus_batch() method: results come back per
+    submitted batch, in submission order through map(), errors surface through the future, and contexts
+    handed in by the caller are not closed."""
+    from mandalorion_b200.poa import PoaPipeline
+    from mandalorion_b200.synth import make_groups
+    from helpers import pack_groups, oracle_consensus_batch
+
+    class Ctx(OracleBackedContext):
+        closed = False
+
+        def close(self):
+            self.closed = True
+
+    batches = [(pack_groups(make_groups("cfg1", 6, first=10 * i)), None) for i in range(5)]
+    ctxs = [Ctx(), Ctx()]
+    with PoaPipeline(contexts=ctxs) as pipe:
+        got = list(pipe.map(batches))
+        bad = pipe.submit()                                               # neither groups nor packed
+        with pytest.raises(Exception):
+            bad.result(timeout=60)
+        again = pipe.submit(packed=batches[0][0]).result(timeout=60)      # the pipeline survives a failed batch
+    for (packed, _), g in zip(batches, got):
+        assert g["cons"] == oracle_consensus_batch(packed=packed)["cons"]
+        assert "wall" in g and g["wall"][1] >= g["wall"][0]
+    assert again["cons"] == got[0]["cons"]
+    assert sum(c.calls for c in ctxs) == 6 and not any(c.closed for c in ctxs)
