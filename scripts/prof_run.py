@@ -13,8 +13,12 @@ from mandalorion_b200.synth import make_packed, GroupConfig
 if cfg == 'cfgS':   # short isoforms: every band fits 128 cells
     cfg = GroupConfig('cfgS', n, 10, 50, 500, 1500, 'loguniform', 0.01, (0.30, 0.35, 0.35))
 packed = make_packed(cfg, n)
+flags = None
+if len(sys.argv) > 4 and sys.argv[4] == "seed":   # every group as `abpoa -S`: only the windowed instantiation launches
+    import numpy as np
+    flags = np.ones(n, np.uint8)
 ctx = PoaContext(0)
-ctx.upload(*packed)
+ctx.upload(*packed, flags=flags)
 for _ in range(reps):
     t0 = time.time()
     st = ctx.run()
