@@ -42,7 +42,7 @@ UNIT = "groups/s"
 WORKLOADS = {
     "cfg1": ("cfg1", 1000, "cfg1: synthetic isoform groups, 3-30 reads, 1-2 kb, 1% R2C2-like error (the D-step config)"),
     "cfg2": ("cfg2", 32768, "cfg2: synthetic isoform groups, 10-50 reads, 0.5-4 kb log-uniform, 1% R2C2-like error"),
-    "cfg3": ("cfg3", 8192, "cfg3: long-isoform stress, 5-30 reads of 5-12 kb, 1% error, wide adaptive band"),
+    "cfg3": ("cfg3", 20000, "cfg3: long-isoform stress, 5-30 reads of 5-12 kb, 1% error, wide adaptive band (the whole 20k-group config per step)"),
     "cfg4": ("cfg4", 8192, "cfg4: high-depth CCS-like groups, 50-200 reads of 2 kb capped to 100 per group (reference subsample)"),
     "cfg4u": ("cfg4", 8192, "cfg4 uncapped: high-depth CCS-like groups, 50-200 reads of 2 kb, every read aligned"),
 }
