@@ -215,15 +215,18 @@ __device__ __forceinline__ int read_step(const KernelArgs &A, const Team<T> &tm,
 
 /* after the last read: heaviest-bundle consensus into the group's region (`fin`: this team finishes a group) */
 template <int T>
-__device__ __forceinline__ int finish_group(const KernelArgs &A, const Team<T> &tm, int slot, const GroupState &G, bool fin, unsigned long long *st) {
+__device__ __forceinline__ int finish_group(const KernelArgs &A, const Team<T> &tm, int slot, const GroupState &G, bool fin, unsigned long long *st,
+                                            int *scratch /* the team's shared memory (free between reads) */) {
     int clen = 0;
     const long long tc0 = clock64();
-    if (fin && tm.tl == 0 && G.N > 2) {       // one lane per team; no cross-lane operation
+    {
+        const bool on = fin && G.N > 2;
         const Slot S = make_slot(A, slot, G.par);
-        const int cap = (int)(A.cons_off[G.g + 1] - A.cons_off[G.g]);
-        clen = heaviest_bundle(A, S, G.N, A.cons + A.cons_off[G.g], cap);
+        const int64_t c0 = on ? A.cons_off[G.g] : 0;
+        const int cap = on ? (int)(A.cons_off[G.g + 1] - c0) : 0;
+        tm.sync();
+        clen = heaviest_bundle<T>(A, S, tm, G.N, A.cons + c0, cap, scratch, on);
     }
-    clen = tm.shfl(clen, 0);
     tm.sync();
     if (!fin) return ST_PENDING;
     if (G.N <= 2) return ST_EMPTY;
@@ -345,7 +348,7 @@ poa_group_kernel(const __grid_constant__ KernelArgs A) {
         if (G.g >= 0 && !act) rc = ST_EMPTY;          // a group without reads
         const bool fin = G.g >= 0 && rc == ST_PENDING && G.r == G.r1;
         if (tm.wany(fin)) {
-            const int frc = finish_group<T>(A, tm, slot, G, fin, gst);
+            const int frc = finish_group<T>(A, tm, slot, G, fin, gst, ring);
             if (fin) rc = frc;
         }
         if (G.g >= 0 && rc != ST_PENDING) {
