@@ -208,7 +208,10 @@ __device__ __forceinline__ int merge_read(const KernelArgs &A, const Slot &S, co
 #ifndef MPOA_MERGE_MK16
 #define MPOA_MERGE_MK16 2
 #endif
-    constexpr int MK = T == 16 ? MPOA_MERGE_MK16 : 2;
+#ifndef MPOA_MERGE_MK32
+#define MPOA_MERGE_MK32 2
+#endif
+    constexpr int MK = T == 16 ? MPOA_MERGE_MK16 : MPOA_MERGE_MK32;
     int32_t *cnt = cnt_p(A, S), *addin = addin_p(A, S), *addout = addout_p(A, S), *srcof = srcof_p(A, S);
     int32_t *pv = pv_p(A, S), *pkey = pkey_p(A, S), *pnew = pnew_p(A, S), *psib = psib_p(A, S);
     int32_t *nin = nin_p(A, S), *nout = nout_p(A, S);
