@@ -165,6 +165,8 @@ static int pick_level(const mpoa_params &p, unsigned level_mask, bool lanes16, i
  */
 struct DevShared {
     std::mutex mu;
+    std::mutex up_mu;          // uploads of one device go one after the other: the first batch's copy gets the whole link and
+                               // its kernels start while the second batch is still copying (instead of both arriving late)
     uint8_t *ws = nullptr;
     size_t ws_bytes = 0;
     int users = 0;
@@ -409,6 +411,7 @@ static int upload_impl(mpoa_ctx *ctx, int64_t n_all, const int64_t *group_read_o
     free_batch(ctx);
     const int64_t n_groups = sel ? n_sel : n_all;
     if (n_groups == 0) return MPOA_OK;
+    std::lock_guard<std::mutex> one_upload_per_device(g_dev[ctx->dev].up_mu);
     if (n_all > INT_MAX / 2) { ctx->err = "too many groups"; return MPOA_EINVAL; }
     const int64_t n_reads_all = group_read_off[n_all];
     if (group_read_off[0] != 0 || n_reads_all < 0) { ctx->err = "group_read_off must start at 0"; return MPOA_EINVAL; }

@@ -103,7 +103,11 @@ def consensus_batch_sharded(packed, devices=None, params=None, flags=None, conte
     straight from the caller's buffer into the pinned staging buffers of its copy, and the results
     back in input order.  No collective, no peer traffic.
 
-    devices: CUDA ordinals (default: all visible).  contexts: optional {device: PoaContext} to reuse.
+    devices: CUDA ordinals (default: all visible).  A device named k times gets k shards and k contexts: their
+    kernels take turns on that GPU while the copies of one shard run beside the kernels of another (the library
+    serialises the uploads of a device, so the first shard's kernels start after HALF of the device's bases have
+    arrived, and its results are fetched while the second shard computes).  contexts: optional
+    {device: PoaContext or [PoaContext, ...]} to reuse.
     Returns dict(cons=[bytes] in input order, status=int32[], stats=[per-device stats dict],
     imbalance=max/mean of the per-device kernel time, owner=int32[] shard of every group)."""
     from .poa import PoaContext, consensus_batch_multi
@@ -115,8 +119,10 @@ def consensus_batch_sharded(packed, devices=None, params=None, flags=None, conte
     use, created = [], []
     try:
         for d in devices:                      # one context per entry: a device named twice gets two
-            c = contexts.get(d) if contexts else None
-            if c is None or any(c is u for u in use):
+            have = contexts.get(d) if contexts else None
+            have = list(have) if isinstance(have, (list, tuple)) else ([have] if have is not None else [])
+            c = next((h for h in have if not any(h is u for u in use)), None)
+            if c is None:
                 c = PoaContext(d, params)
                 created.append(c)
             use.append(c)

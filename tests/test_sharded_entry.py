@@ -108,3 +108,22 @@ def test_multi_reports_a_too_small_result_buffer(gpu_ctx):
     p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
     rc = lib.mpoa_consensus_batch_multi(handles, 1, ng, p(gro), p(rbo), p(bases), None, p(off), p(buf), 4, p(status), None, None)
     assert rc == -4 and off[ng] == sum(len(c) for c in oracle_consensus_batch(packed=(gro, rbo, bases))["cons"])
+
+
+@pytest.mark.gpu
+def test_two_shards_on_one_gpu_through_the_sharded_entry(gpu_ctx):
+    """a device named twice: two shards, two contexts, kernels taking turns -- same answers, input order"""
+    from mandalorion_b200 import PoaContext
+    from mandalorion_b200.shard import consensus_batch_sharded
+    packed = pack_groups(make_groups(CFG))
+    want = oracle_consensus_batch(packed=packed)
+    other = PoaContext(0)
+    try:
+        out = consensus_batch_sharded(packed, devices=[0, 0], contexts={0: [gpu_ctx, other]})
+        assert out["cons"] == want["cons"] and list(out["status"]) == list(want["status"])
+        assert len(out["stats"]) == 2 and set(out["owner"].tolist()) == {0, 1}
+        assert sum(s["band_cells"] for s in out["stats"]) == want["stats"]["band_cells"]
+        again = consensus_batch_sharded(packed, devices=[0, 0])          # contexts created and closed by the call
+        assert again["cons"] == want["cons"]
+    finally:
+        other.close()
