@@ -365,7 +365,6 @@ class PoaPipeline:
             if not fut.set_running_or_notify_cancel():
                 continue
             try:
-                import time
                 t0 = time.perf_counter()
                 res = ctx.consensus_batch(**kw)
                 res["wall"] = (t0, time.perf_counter())      # when this batch was in its context (perf_counter)
