@@ -14,9 +14,14 @@ config.  Default = cfg2 (configs[1]: 10-50 reads, 0.5-4 kb, ~1 % R2C2-like error
                                        over the N GPUs (rank 0 drives them), results gathered in input order
   --dstep                              cfg1 through the reference's function boundary: prepare_group
                                        (subsample + orientation) -> one GPU batch -> file writer
+  --pipeline D                         contexts of the pipelined e2e leg (default 2; 1 = serial calls only)
+  --shards-per-gpu K                   strong scaling: K shards (contexts) per GPU (default 1)
 
   value      groups/s, whole job, inputs resident in HBM (mpoa_batch_run only, CUDA events)
-  e2e        groups/s through PoaContext.consensus_batch() with pinned HOST buffers in and out
+  e2e        groups/s through PoaContext.consensus_batch() with pinned HOST buffers in and out: measured as one
+             call after the other AND with the same calls through PoaPipeline (two batches in flight: the copies
+             of one beside the kernels of the other; every copy of every step inside the timed region); the
+             line carries both, e2e.value is the better one and e2e.mode names it
   roofline   HBM: algorithmic bytes (1 B traceback per band cell + 1 B/base in + 1 B/base out)
              over the kernel time; int_roofline: algorithmic integer ops over the INT-pipe peak
   cpu_baseline / --impl reference: the CPU port of the reference's abpoa path (oracle/, a SCALAR
